@@ -1,0 +1,47 @@
+/*
+ * p264b200_host.h -- host-side (CPU) half of the drop-in: the syntax front-end that turns
+ * NAL units into FrameSyntax buffers, plus small bitstream utilities.  No GPU needed.
+ *
+ * Replaces, on the host, decoder/set.c, decoder/decoder.c:70-301,368-593,
+ * decoder/macroblock.c:72-597, decoder/dec_cavlc.c, decoder/lists.c and the predictor /
+ * cache parts of core/macroblock.c:40-252,870-1340 of the reference.
+ */
+#ifndef P264B200_HOST_H
+#define P264B200_HOST_H
+
+#include "p264b200_recon.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p264b200_parser p264b200_parser;
+
+/* pinned != 0: FrameSyntax buffers live in page-locked memory (needs a CUDA device) */
+p264b200_parser *p264b200_parser_open(int pinned, int verbose);
+void p264b200_parser_close(p264b200_parser *p);
+
+/* One NAL unit in p264_nal_t form (header byte stripped, emulation prevention removed).
+ * On a completed picture *got_frame = 1 and *out points at parser-owned buffers that stay
+ * valid until the next call.  Returns 0 or a negative P264B200_E* code. */
+int p264b200_parser_nal(p264b200_parser *p, int nal_type, int nal_ref_idc, const uint8_t *payload, int size,
+                        p264b200_frame_syntax *out, int *got_frame);
+int p264b200_parser_geometry(const p264b200_parser *p, int *mb_w, int *mb_h, int *ring_size);
+
+/* Annex-B byte-stream splitter (replaces the start-code FSM of p264decoder.c:259-301, without
+ * its 3 MB NAL limit).  *pos is the scan cursor; on return 1, [*nal_start, *nal_start+*nal_size)
+ * is the next NAL unit (header byte included, trailing zero bytes of the next start code
+ * excluded the same way the reference CLI excludes them).  Returns 0 at end of buffer. */
+int p264b200_annexb_next(const uint8_t *buf, size_t size, size_t *pos, size_t *nal_start, size_t *nal_size);
+
+/* p264_nal_decode semantics (core/core.c:306-331) on raw pointers */
+int p264b200_nal_unescape(const uint8_t *src, int size, uint8_t *dst, int *nal_type, int *nal_ref_idc);
+
+/* raw CAVLC code tables for self-checks: kind 0 coeff_token[nC class], 1 chroma-DC coeff_token,
+ * 2 total_zeros[total_coeff-1], 3 chroma-DC total_zeros, 4 run_before[min(zeros_left,7)-1] */
+int p264b200_cavlc_table_entry(int kind, int table, int sym, int *len, int *bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,181 @@
+/*
+ * p264b200_recon.h -- frame-level C-ABI of the B200 macroblock reconstruction engine.
+ *
+ * This is the real hot-path boundary: the host (entropy decode, MV prediction)
+ * fills one FrameSyntax per picture and hands it to the GPU, which runs everything
+ * the reference does below decoder/macroblock.c:599 for that picture:
+ *
+ *   reference call                                     replaced by
+ *   ------------------------------------------------   -------------------------------
+ *   p264_macroblock_decode      decoder/macroblock.c:755   recon_inter / recon_intra kernels
+ *   p264_macroblock_decode_skip decoder/macroblock.c:895   recon_inter kernel (P_SKIP = 16x16, no residual)
+ *   p264_mb_mc                  core/macroblock.c:633      recon_inter kernel (MC from mv[16]/ref[4])
+ *   p264_frame_deblocking_filter core/frame.c:490          deblock kernel
+ *   p264_frame_expand_border    core/frame.c:205           border kernel
+ *   p264_frame_filter           core/mc.c:409              eliminated (6-tap on the fly)
+ *
+ * Plain C, no torch / CUDA types in any signature.  Every entry point returns
+ * 0 on success or a negative P264B200_E* code and never aborts the host.
+ */
+#ifndef P264B200_RECON_H
+#define P264B200_RECON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P264B200_ABI_VERSION 1
+
+/* error codes */
+#define P264B200_OK          0
+#define P264B200_EINVAL     (-1)  /* bad argument */
+#define P264B200_ENODEV     (-2)  /* no usable CUDA device: there is NO CPU fallback */
+#define P264B200_ECUDA      (-3)  /* CUDA runtime error (see p264b200_last_error) */
+#define P264B200_ENOMEM     (-4)
+#define P264B200_EUNSUP     (-5)  /* syntax the reference cannot decode either */
+#define P264B200_EBITSTREAM (-6)
+
+/* macroblock classes (the subset core/macroblock.h:42-65 that the decoder reaches) */
+enum {
+    P264B200_MB_I4x4   = 0,
+    P264B200_MB_I16x16 = 1,
+    P264B200_MB_P_L0   = 2,   /* 16x16 / 16x8 / 8x16 */
+    P264B200_MB_P_8x8  = 3,
+    P264B200_MB_P_SKIP = 4
+};
+#define P264B200_IS_INTRA(t) ((t) <= P264B200_MB_I16x16)
+
+enum { P264B200_SLICE_P = 0, P264B200_SLICE_I = 2 };
+
+/* partition shapes, informational (MC is driven by mv[]/ref[] alone) */
+enum { P264B200_D_16x16 = 0, P264B200_D_16x8 = 1, P264B200_D_8x16 = 2, P264B200_D_8x8 = 3 };
+enum { P264B200_SUB_8x8 = 0, P264B200_SUB_8x4 = 1, P264B200_SUB_4x8 = 2, P264B200_SUB_4x4 = 3 };
+
+/*
+ * One macroblock of side information: exactly the fields p264_macroblock_decode and
+ * p264_frame_deblocking_filter read from h->mb / the per-frame arrays written by
+ * p264_macroblock_cache_save (core/macroblock.c:1234-1340).  96 bytes, all 4x4-block
+ * indexed fields are in RASTER order inside the MB (b = 4*y + x), not the bitstream
+ * z-order.
+ */
+typedef struct p264b200_mb {
+    int16_t  mv[16][2];    /* qpel list-0 MV of every 4x4 block; 0 for intra                    */
+    int8_t   ref[4];       /* list-0 index of every 8x8 (raster); -1 for intra                   */
+    uint8_t  mb_type;      /* P264B200_MB_*                                                      */
+    uint8_t  qp;           /* luma QP used for dequant (decoder/macroblock.c:568,578)            */
+    uint8_t  qp_dbf;       /* QP the deblocker sees: last-QP rule of core/macroblock.c:1247-1252 */
+    uint8_t  cbp_chroma;   /* 0 none, 1 DC only, 2 DC+AC                                         */
+    uint16_t luma_mask;    /* bit b: luma 4x4 block b has total_coeff>0 and 16 coefs in the stream */
+    uint8_t  i16_mode;     /* raw intra16x16 mode 0..3 (V,H,DC,P)                                */
+    uint8_t  chroma_mode;  /* raw intra chroma mode 0..3 (DC,H,V,P)                              */
+    uint8_t  i4_mode[8];   /* 16 nibbles, raster order, low nibble first: raw 4x4 mode 0..8      */
+    uint32_t coef_off;     /* offset of this MB's chunk in the coefficient stream, int16 units   */
+    uint8_t  chroma_mask;  /* bit i: chroma AC block i (0-3 Cb, 4-7 Cr, raster) present          */
+    uint8_t  part;         /* P264B200_D_*                                                       */
+    uint8_t  sub_part[4];  /* P264B200_SUB_* per 8x8                                             */
+    uint8_t  reserved[2];
+} p264b200_mb;
+
+/*
+ * Coefficient stream: int16, zig-zag order exactly as the CAVLC reader produced
+ * them (decoder/dec_cavlc.c:1514-1520) truncated to 16 bit the way the reference's
+ * unscan does (decoder/macroblock.c:605-630).  Chunk of one MB, in this order:
+ *   [I16x16 only]         16  luma DC levels
+ *   for each set bit b of luma_mask, ascending:  16 levels
+ *                          (I16x16: slot 0 is 0 and slots 1..15 are the 15 AC levels)
+ *   [cbp_chroma != 0]     4 Cb DC levels, 4 Cr DC levels (raster 2x2)
+ *   for each set bit i of chroma_mask, ascending: 16 levels (slot 0 = 0, 1..15 AC)
+ * Every chunk starts on an 8-element (16-byte) boundary.
+ */
+
+typedef struct p264b200_frame_hdr {
+    int32_t  mb_w, mb_h;
+    int32_t  slice_type;              /* P264B200_SLICE_*                                     */
+    int32_t  deblock;                 /* 0 = filter off (disable_deblocking_filter_idc == 1)   */
+    int32_t  alpha_c0_offset;         /* as the reference uses them: the raw, UN-doubled        */
+    int32_t  beta_offset;             /*   slice header values (decoder/decoder.c:177-178)      */
+    int32_t  chroma_qp_index_offset;
+    int32_t  num_ref;                 /* size of list 0                                         */
+    int32_t  ref_slot[16];            /* list-0 index -> frame-ring slot                        */
+    int32_t  dst_slot;                /* ring slot this picture is reconstructed into           */
+    int32_t  n_intra;                 /* number of intra MBs (0 lets the engine skip the wavefront) */
+    uint32_t n_coef;                  /* int16 elements in the coefficient stream               */
+    int32_t  reserved[4];
+} p264b200_frame_hdr;
+
+typedef struct p264b200_frame_syntax {
+    p264b200_frame_hdr hdr;
+    const p264b200_mb *mbs;           /* mb_w*mb_h records, raster                             */
+    const int16_t     *coefs;         /* n_coef levels                                         */
+} p264b200_frame_syntax;
+
+/* ------------------------------------------------------------------------- *
+ * Engine: L independent lanes (streams / closed GOPs) reconstructed per launch
+ * ------------------------------------------------------------------------- */
+typedef struct p264b200_engine p264b200_engine;
+
+typedef struct p264b200_engine_cfg {
+    int32_t  device;                  /* CUDA ordinal                                          */
+    int32_t  lanes;                   /* independent streams batched per launch                */
+    int32_t  mb_w, mb_h;
+    int32_t  n_slots;                 /* frame ring size per lane = num_ref_frames + 1          */
+    uint32_t coef_capacity;           /* int16 per lane per frame (0 = dense worst case)        */
+    int32_t  stage_steps;             /* frames per lane that can be pre-staged in HBM (>=1)    */
+    uint32_t flags;
+} p264b200_engine_cfg;
+
+const char *p264b200_last_error(void);
+int  p264b200_abi_version(void);
+int  p264b200_device_count(void);
+
+int  p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg);
+void p264b200_engine_destroy(p264b200_engine *e);
+
+/* geometry of the padded device frame store (for upload/download helpers) */
+int  p264b200_engine_geometry(const p264b200_engine *e, int32_t *luma_stride, int32_t *chroma_stride,
+                              int32_t *width, int32_t *height);
+
+/* Copy one picture's syntax from HOST memory into staging step `step` of lane `lane`
+ * (asynchronous on the engine stream when the source is pinned). */
+int  p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs);
+
+/* Reconstruct staging step `step` for lanes [0, n_lanes): MC + IDCT + intra + deblock + border.
+ * Asynchronous; inputs are already resident in HBM. */
+int  p264b200_recon_step(p264b200_engine *e, int step, int n_lanes);
+
+/* Convenience for the serial decoder: stage + reconstruct one picture on one lane. */
+int  p264b200_recon_frame(p264b200_engine *e, int lane, const p264b200_frame_syntax *fs);
+
+/* Picture transfer, tight (unpadded) I420 planes on the host side. Asynchronous on
+ * the engine stream; call p264b200_engine_sync before reading host memory. */
+int  p264b200_frame_upload(p264b200_engine *e, int lane, int slot,
+                           const uint8_t *y, int y_stride, const uint8_t *u, const uint8_t *v, int c_stride);
+int  p264b200_frame_download(p264b200_engine *e, int lane, int slot,
+                             uint8_t *y, int y_stride, uint8_t *u, uint8_t *v, int c_stride);
+
+int  p264b200_engine_sync(p264b200_engine *e);
+
+/* CUDA stream the engine launches on (cudaStream_t as void*), for external event timing */
+void *p264b200_engine_stream(p264b200_engine *e);
+
+/* Device-side event timing on the engine stream (milliseconds). */
+int  p264b200_timer_start(p264b200_engine *e);
+int  p264b200_timer_stop(p264b200_engine *e, float *ms);
+/* Per-kernel accumulated device time since the last reset (CUDA events around each launch;
+ * only collected when profiling is enabled, which serialises nothing but adds events). */
+int  p264b200_profile_enable(p264b200_engine *e, int on);
+int  p264b200_profile_read(p264b200_engine *e, float ms_out[8], uint64_t launches_out[8]);
+/* number of kernel launches issued by the engine since creation */
+uint64_t p264b200_engine_launches(const p264b200_engine *e);
+
+/* pinned host memory helpers for the callers that pack FrameSyntax */
+void *p264b200_host_alloc(size_t bytes);
+void  p264b200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P264B200_RECON_H */
