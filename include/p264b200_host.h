@@ -14,6 +14,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef struct p264b200_parser p264b200_parser;
 
@@ -41,6 +44,9 @@ int p264b200_nal_unescape(const uint8_t *src, int size, uint8_t *dst, int *nal_t
  * 2 total_zeros[total_coeff-1], 3 chroma-DC total_zeros, 4 run_before[min(zeros_left,7)-1] */
 int p264b200_cavlc_table_entry(int kind, int table, int sym, int *len, int *bits);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

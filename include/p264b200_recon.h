@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 #define P264B200_ABI_VERSION 1
 
@@ -175,6 +178,9 @@ uint64_t p264b200_engine_launches(const p264b200_engine *e);
 void *p264b200_host_alloc(size_t bytes);
 void  p264b200_host_free(void *p);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

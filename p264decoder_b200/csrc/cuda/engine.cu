@@ -1,0 +1,401 @@
+// Host side of the frame-level C-ABI (include/p264b200_recon.h): device frame ring, syntax
+// staging and the per-picture kernel sequence that replaces p264_slice_decode steps [3]-[4]
+// (decoder/decoder.c:623-661).  There is deliberately no CPU path in this file: without a
+// usable CUDA device every entry point fails with P264B200_ENODEV.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "border.cuh"
+#include "common.cuh"
+#include "deblock.cuh"
+#include "recon_inter.cuh"
+#include "recon_intra.cuh"
+
+using namespace p264b200;
+
+namespace {
+thread_local char g_err[512] = "";
+void set_err(const char *what, cudaError_t e)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) {                  \
+            set_err(#call, e_);                   \
+            return P264B200_ECUDA;                \
+        }                                         \
+    } while (0)
+
+enum { K_INTER = 0, K_INTRA, K_DEBLOCK, K_BORDER, K_COUNT };
+}  // namespace
+
+struct p264b200_engine {
+    p264b200_engine_cfg cfg;
+    Geometry g;
+    cudaStream_t stream = nullptr;
+    // frame store
+    uint8_t *d_y = nullptr, *d_c = nullptr;
+    // staging: [step][lane]
+    p264b200_mb *d_mbs = nullptr;
+    int16_t *d_coefs = nullptr;
+    FrameDesc *d_descs = nullptr, *h_descs = nullptr;
+    size_t coef_cap = 0;  // int16 per lane per step
+    int *d_sync = nullptr;  // [4 tickets/pad][lanes][2*mb_h]
+    size_t sync_bytes = 0;
+    std::vector<uint8_t> slot_flags;  // [step][lane]: bit0 intra MBs present, bit1 deblock on, bit2 P slice
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    std::vector<int> prof_kind;
+    size_t prof_used = 0;
+    float prof_ms[K_COUNT] = {0, 0, 0, 0};
+    uint64_t prof_n[K_COUNT] = {0, 0, 0, 0};
+    uint64_t launches = 0;
+
+    uint8_t *plane(int lane, int slot, int c) const
+    {
+        const size_t f = (size_t)lane * cfg.n_slots + slot;
+        if (c == 0) return d_y + f * g.y_plane + (size_t)kLumaPad * g.y_stride + kLumaPad;
+        return d_c + (f * 2 + (c - 1)) * g.c_plane + (size_t)kChromaPad * g.c_stride + kChromaPad;
+    }
+};
+
+namespace {
+
+struct ProfScope {
+    p264b200_engine *e;
+    int kind;
+    size_t idx = 0;
+    bool on;
+    ProfScope(p264b200_engine *e_, int k) : e(e_), kind(k), on(e_->profile)
+    {
+        e->launches++;
+        if (!on) return;
+        if (e->prof_used + 2 > e->prof_ev.size()) {
+            for (int i = 0; i < 2; i++) {
+                cudaEvent_t ev;
+                cudaEventCreate(&ev);
+                e->prof_ev.push_back(ev);
+            }
+            e->prof_kind.push_back(kind);
+        }
+        idx = e->prof_used;
+        e->prof_kind[idx / 2] = kind;
+        e->prof_used += 2;
+        cudaEventRecord(e->prof_ev[idx], e->stream);
+    }
+    ~ProfScope()
+    {
+        if (on) cudaEventRecord(e->prof_ev[idx + 1], e->stream);
+    }
+};
+
+void prof_collect(p264b200_engine *e)
+{
+    for (size_t i = 0; i + 1 < e->prof_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->prof_ev[i], e->prof_ev[i + 1]) == cudaSuccess) {
+            e->prof_ms[e->prof_kind[i / 2]] += ms;
+            e->prof_n[e->prof_kind[i / 2]]++;
+        }
+    }
+    e->prof_used = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *p264b200_last_error(void) { return g_err; }
+int p264b200_abi_version(void) { return P264B200_ABI_VERSION; }
+
+int p264b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *p264b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void p264b200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void p264b200_engine_destroy(p264b200_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_y);
+    cudaFree(e->d_c);
+    cudaFree(e->d_mbs);
+    cudaFree(e->d_coefs);
+    cudaFree(e->d_descs);
+    cudaFree(e->d_sync);
+    if (e->h_descs) cudaFreeHost(e->h_descs);
+    for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg)
+{
+    if (!out || !cfg || cfg->lanes < 1 || cfg->mb_w < 1 || cfg->mb_h < 1 || cfg->n_slots < 1 || cfg->n_slots > 17 ||
+        cfg->stage_steps < 1) {
+        set_err("p264b200_engine_create: bad configuration", cudaSuccess);
+        return P264B200_EINVAL;
+    }
+    if (p264b200_device_count() <= cfg->device) {
+        set_err("p264b200_engine_create: no CUDA device (this engine has no CPU fallback)", cudaSuccess);
+        return P264B200_ENODEV;
+    }
+    CK(cudaSetDevice(cfg->device));
+    p264b200_engine *e = new (std::nothrow) p264b200_engine;
+    if (!e) return P264B200_ENOMEM;
+    e->cfg = *cfg;
+    Geometry &g = e->g;
+    g.mb_w = cfg->mb_w;
+    g.mb_h = cfg->mb_h;
+    g.width = 16 * cfg->mb_w;
+    g.height = 16 * cfg->mb_h;
+    g.y_stride = (g.width + 2 * kLumaPad + 127) & ~127;
+    g.c_stride = g.y_stride / 2;
+    g.y_rows = g.height + 2 * kLumaPad;
+    g.c_rows = g.height / 2 + 2 * kChromaPad;
+    g.y_plane = (size_t)g.y_stride * g.y_rows;
+    g.c_plane = (size_t)g.c_stride * g.c_rows;
+    const size_t n_mb = (size_t)g.mb_w * g.mb_h;
+    e->coef_cap = cfg->coef_capacity ? cfg->coef_capacity : n_mb * 408;
+    e->coef_cap = (e->coef_cap + 7) & ~(size_t)7;
+    const size_t frames = (size_t)cfg->lanes * cfg->n_slots;
+    const size_t slots = (size_t)cfg->stage_steps * cfg->lanes;
+    e->sync_bytes = (4 + (size_t)cfg->lanes * 2 * g.mb_h) * sizeof(int);
+    int rc = P264B200_OK;
+    auto fail = [&](const char *what, cudaError_t err) {
+        set_err(what, err);
+        rc = err == cudaErrorMemoryAllocation ? P264B200_ENOMEM : P264B200_ECUDA;
+    };
+    cudaError_t err;
+    if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
+    if (!rc && (err = cudaMalloc(&e->d_y, frames * g.y_plane)) != cudaSuccess) fail("cudaMalloc luma store", err);
+    if (!rc && (err = cudaMalloc(&e->d_c, frames * 2 * g.c_plane)) != cudaSuccess) fail("cudaMalloc chroma store", err);
+    if (!rc && (err = cudaMalloc(&e->d_mbs, slots * n_mb * sizeof(p264b200_mb))) != cudaSuccess) fail("cudaMalloc mbs", err);
+    if (!rc && (err = cudaMalloc(&e->d_coefs, slots * e->coef_cap * sizeof(int16_t))) != cudaSuccess) fail("cudaMalloc coefs", err);
+    if (!rc && (err = cudaMalloc(&e->d_descs, slots * sizeof(FrameDesc))) != cudaSuccess) fail("cudaMalloc descs", err);
+    if (!rc && (err = cudaMallocHost(&e->h_descs, slots * sizeof(FrameDesc))) != cudaSuccess) fail("cudaMallocHost descs", err);
+    if (!rc && (err = cudaMalloc(&e->d_sync, e->sync_bytes)) != cudaSuccess) fail("cudaMalloc sync", err);
+    if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
+    if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
+    if (!rc) {
+        // grey frames so that never-written slots are deterministic
+        if ((err = cudaMemsetAsync(e->d_y, 128, frames * g.y_plane, e->stream)) != cudaSuccess) fail("memset", err);
+        if (!rc && (err = cudaMemsetAsync(e->d_c, 128, frames * 2 * g.c_plane, e->stream)) != cudaSuccess) fail("memset", err);
+        if (!rc && (err = cudaStreamSynchronize(e->stream)) != cudaSuccess) fail("sync", err);
+    }
+    if (rc) {
+        p264b200_engine_destroy(e);
+        return rc;
+    }
+    memset(e->h_descs, 0, slots * sizeof(FrameDesc));
+    e->slot_flags.assign(slots, 0);
+    *out = e;
+    return P264B200_OK;
+}
+
+int p264b200_engine_geometry(const p264b200_engine *e, int32_t *luma_stride, int32_t *chroma_stride, int32_t *width,
+                             int32_t *height)
+{
+    if (!e) return P264B200_EINVAL;
+    if (luma_stride) *luma_stride = e->g.y_stride;
+    if (chroma_stride) *chroma_stride = e->g.c_stride;
+    if (width) *width = e->g.width;
+    if (height) *height = e->g.height;
+    return P264B200_OK;
+}
+
+int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs)
+{
+    if (!e || !fs || step < 0 || step >= e->cfg.stage_steps || lane < 0 || lane >= e->cfg.lanes) return P264B200_EINVAL;
+    const p264b200_frame_hdr &h = fs->hdr;
+    const Geometry &g = e->g;
+    if (h.mb_w != g.mb_w || h.mb_h != g.mb_h || h.dst_slot < 0 || h.dst_slot >= e->cfg.n_slots || h.num_ref < 0 ||
+        h.num_ref > kMaxRefs || h.n_coef > e->coef_cap || !fs->mbs || (h.n_coef && !fs->coefs)) {
+        set_err("p264b200_stage_frame: syntax does not fit the engine", cudaSuccess);
+        return P264B200_EINVAL;
+    }
+    if (h.slice_type == P264B200_SLICE_P && h.num_ref < 1) return P264B200_EINVAL;
+    for (int i = 0; i < h.num_ref; i++)
+        if (h.ref_slot[i] < 0 || h.ref_slot[i] >= e->cfg.n_slots) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t n_mb = (size_t)g.mb_w * g.mb_h;
+    const size_t s = (size_t)step * e->cfg.lanes + lane;
+    p264b200_mb *d_mbs = e->d_mbs + s * n_mb;
+    int16_t *d_coefs = e->d_coefs + s * e->coef_cap;
+    CK(cudaMemcpyAsync(d_mbs, fs->mbs, n_mb * sizeof(p264b200_mb), cudaMemcpyHostToDevice, e->stream));
+    if (h.n_coef)
+        CK(cudaMemcpyAsync(d_coefs, fs->coefs, (size_t)h.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+    FrameDesc &d = e->h_descs[s];
+    memset(&d, 0, sizeof(d));
+    d.mbs = d_mbs;
+    d.coefs = d_coefs;
+    for (int c = 0; c < 3; c++) d.cur[c] = e->plane(lane, h.dst_slot, c);
+    for (int i = 0; i < h.num_ref; i++)
+        for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
+    d.row_progress = e->d_sync + 4 + (size_t)lane * 2 * g.mb_h;
+    d.slice_type = h.slice_type;
+    d.deblock = h.deblock;
+    d.alpha_off = h.alpha_c0_offset;
+    d.beta_off = h.beta_offset;
+    d.chroma_qp_off = h.chroma_qp_index_offset;
+    d.n_intra = h.n_intra;
+    d.num_ref = h.num_ref;
+    CK(cudaMemcpyAsync(e->d_descs + s, &d, sizeof(FrameDesc), cudaMemcpyHostToDevice, e->stream));
+    e->slot_flags[s] = (uint8_t)((h.n_intra > 0) | ((h.deblock != 0) << 1) | ((h.slice_type == P264B200_SLICE_P) << 2));
+    return P264B200_OK;
+}
+
+int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
+{
+    if (!e || step < 0 || step >= e->cfg.stage_steps || n_lanes < 1 || n_lanes > e->cfg.lanes) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const Geometry &g = e->g;
+    const int n_mb = g.mb_w * g.mb_h;
+    const FrameDesc *descs = e->d_descs + (size_t)step * e->cfg.lanes;
+    unsigned flags = 0;
+    for (int l = 0; l < n_lanes; l++) flags |= e->slot_flags[(size_t)step * e->cfg.lanes + l];
+    const bool intra = flags & 1, dbf = flags & 2, pslice = flags & 4;
+    if (intra || dbf) CK(cudaMemsetAsync(e->d_sync, 0, e->sync_bytes, e->stream));
+    if (pslice) {
+        ProfScope p(e, K_INTER);
+        dim3 grid((n_mb + kMbPerCta - 1) / kMbPerCta, n_lanes);
+        recon_inter_kernel<<<grid, kInterThreads, 0, e->stream>>>(descs, g);
+    }
+    if (intra) {
+        ProfScope p(e, K_INTRA);
+        recon_intra_kernel<<<g.mb_h * n_lanes, 32, 0, e->stream>>>(descs, g, e->d_sync + 0);
+    }
+    if (dbf) {
+        ProfScope p(e, K_DEBLOCK);
+        deblock_kernel<<<g.mb_h * n_lanes, 32, 0, e->stream>>>(descs, g, e->d_sync + 1);
+    }
+    {
+        ProfScope p(e, K_BORDER);
+        const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
+                          2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
+        dim3 grid((words + 255) / 256, n_lanes);
+        border_kernel<<<grid, 256, 0, e->stream>>>(descs, g, nullptr, nullptr, nullptr);
+    }
+    CK(cudaGetLastError());
+    return P264B200_OK;
+}
+
+int p264b200_recon_frame(p264b200_engine *e, int lane, const p264b200_frame_syntax *fs)
+{
+    // the one-picture convenience path is for the serial decoder (lane 0 only); batched callers
+    // stage every lane and call p264b200_recon_step
+    if (!e || lane != 0) return P264B200_EINVAL;
+    int r = p264b200_stage_frame(e, 0, 0, fs);
+    if (r) return r;
+    return p264b200_recon_step(e, 0, 1);
+}
+
+int p264b200_frame_upload(p264b200_engine *e, int lane, int slot, const uint8_t *y, int y_stride, const uint8_t *u,
+                          const uint8_t *v, int c_stride)
+{
+    if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const Geometry &g = e->g;
+    CK(cudaMemcpy2DAsync(e->plane(lane, slot, 0), g.y_stride, y, y_stride, g.width, g.height, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpy2DAsync(e->plane(lane, slot, 1), g.c_stride, u, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpy2DAsync(e->plane(lane, slot, 2), g.c_stride, v, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
+    const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
+                      2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
+    e->launches++;
+    border_kernel<<<dim3((words + 255) / 256, 1), 256, 0, e->stream>>>(nullptr, g, e->plane(lane, slot, 0), e->plane(lane, slot, 1),
+                                                                      e->plane(lane, slot, 2));
+    CK(cudaGetLastError());
+    return P264B200_OK;
+}
+
+int p264b200_frame_download(p264b200_engine *e, int lane, int slot, uint8_t *y, int y_stride, uint8_t *u, uint8_t *v,
+                            int c_stride)
+{
+    if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const Geometry &g = e->g;
+    CK(cudaMemcpy2DAsync(y, y_stride, e->plane(lane, slot, 0), g.y_stride, g.width, g.height, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpy2DAsync(u, c_stride, e->plane(lane, slot, 1), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpy2DAsync(v, c_stride, e->plane(lane, slot, 2), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->stream));
+    return P264B200_OK;
+}
+
+int p264b200_engine_sync(p264b200_engine *e)
+{
+    if (!e) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->profile) prof_collect(e);
+    return P264B200_OK;
+}
+
+void *p264b200_engine_stream(p264b200_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int p264b200_timer_start(p264b200_engine *e)
+{
+    if (!e) return P264B200_EINVAL;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    return P264B200_OK;
+}
+int p264b200_timer_stop(p264b200_engine *e, float *ms)
+{
+    if (!e || !ms) return P264B200_EINVAL;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaEventSynchronize(e->ev1));
+    CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    if (e->profile) prof_collect(e);
+    return P264B200_OK;
+}
+
+int p264b200_profile_enable(p264b200_engine *e, int on)
+{
+    if (!e) return P264B200_EINVAL;
+    e->profile = on != 0;
+    e->prof_used = 0;
+    for (int i = 0; i < K_COUNT; i++) e->prof_ms[i] = 0, e->prof_n[i] = 0;
+    return P264B200_OK;
+}
+int p264b200_profile_read(p264b200_engine *e, float ms_out[8], uint64_t launches_out[8])
+{
+    if (!e || !ms_out || !launches_out) return P264B200_EINVAL;
+    for (int i = 0; i < 8; i++) {
+        ms_out[i] = i < K_COUNT ? e->prof_ms[i] : 0.f;
+        launches_out[i] = i < K_COUNT ? e->prof_n[i] : 0;
+    }
+    return P264B200_OK;
+}
+uint64_t p264b200_engine_launches(const p264b200_engine *e) { return e ? e->launches : 0; }
+
+}  // extern "C"

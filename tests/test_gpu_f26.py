@@ -1,0 +1,58 @@
+"""GPU: config 2 of BASELINE.json -- bin/f26.264 with host entropy decode + GPU reconstruction,
+YUV byte-identical to the reference decoder's golden (and to the CPU oracle, frame by frame)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import p264decoder_b200 as P
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mismatch_report(fr, got, want):
+    msgs = []
+    for name, g, w, s in zip("YUV", got, want, (16, 8, 8)):
+        bad = np.argwhere(g != w)
+        if len(bad):
+            mbs = sorted({(int(r) // s, int(c) // s) for r, c in bad})[:6]
+            kinds = [(my, mx, int(fr.mbs["mb_type"][my * fr.hdr.mb_w + mx])) for my, mx in mbs]
+            msgs.append(f"{name}: {len(bad)} samples, first MBs (y,x,type) {kinds}")
+    return "; ".join(msgs)
+
+
+def test_f26_gpu_bit_exact():
+    path = O.f26_path()
+    if path is None:
+        pytest.skip("oracle/_ref/f26.264 not present")
+    data = np.fromfile(path, dtype=np.uint8)
+    golden = O.f26_frame_md5s()
+    frames = list(P.Parser(verbose=False).parse_stream(data))
+    ring = O.OracleFrames(22, 18, 2)
+    eng = P.Engine(22, 18, n_slots=2)
+    whole = hashlib.md5()
+    for i, fr in enumerate(frames):
+        want = ring.recon(fr)
+        eng.recon_frame(fr.syntax())
+        got = eng.download(0, fr.hdr.dst_slot)
+        ok = all(np.array_equal(g, w) for g, w in zip(got, want))
+        assert ok, f"frame {i} (slice {fr.hdr.slice_type}): GPU != oracle: " + _mismatch_report(fr, got, want)
+        assert O.i420_md5(*got) == golden[i]
+        for p in got:
+            whole.update(p.tobytes())
+    assert whole.hexdigest() == "a482adab07324894b443e081a84ee1df"
+    assert eng.launches > 0
+
+
+def test_f26_decode_annexb_api():
+    path = O.f26_path()
+    if path is None:
+        pytest.skip("oracle/_ref/f26.264 not present")
+    data = np.fromfile(path, dtype=np.uint8)
+    golden = O.f26_frame_md5s()
+    n = 0
+    for n, (y, u, v) in enumerate(P.decode_annexb(data)):
+        if n < 12 or n % 25 == 0:
+            assert O.i420_md5(y, u, v) == golden[n]
+    assert n == 299
