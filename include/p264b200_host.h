@@ -44,6 +44,37 @@ int p264b200_nal_unescape(const uint8_t *src, int size, uint8_t *dst, int *nal_t
  * 2 total_zeros[total_coeff-1], 3 chroma-DC total_zeros, 4 run_before[min(zeros_left,7)-1] */
 int p264b200_cavlc_table_entry(int kind, int table, int sym, int *len, int *bits);
 
+/* ------------------------------------------------------------------------- *
+ * Synthetic stream generator (BASELINE.json configs 3-5): emits FrameSyntax for a
+ * stream of random P pictures (optionally after one intra picture).  Deterministic
+ * for a given cfg.  Not part of the reference (which ships no generator or tests).
+ * ------------------------------------------------------------------------- */
+typedef struct p264b200_synth p264b200_synth;
+typedef struct p264b200_synth_cfg {
+    int32_t  mb_w, mb_h;
+    int32_t  n_refs;            /* reference frames (ring = n_refs + 1 slots), ref_idx uniform per partition */
+    uint64_t seed;
+    int32_t  qp_min, qp_max, qp_step;  /* slice QP cycles qp_min, qp_min+step, ... per picture */
+    int32_t  coded_pct;         /* % of 4x4 luma blocks with residual                                   */
+    int32_t  max_level;         /* |level| bound                                                        */
+    int32_t  mv_range;          /* integer MV part uniform in +-mv_range samples, all 16 quarter phases */
+    int32_t  sub8x8;            /* allow 8x4 / 4x8 / 4x4 sub-partitions                                 */
+    int32_t  intra_pct;         /* % intra MBs inside P pictures                                        */
+    int32_t  skip_pct;          /* % P_SKIP                                                             */
+    int32_t  deblock;
+    int32_t  sweep_offsets;     /* random alpha/beta offsets in [-6,6] per picture                      */
+    int32_t  chroma_qp_index_offset;
+    int32_t  confine_mv;        /* keep referenced samples inside the reference's 32-sample border      */
+    int32_t  first_intra;       /* picture 0 is an all-intra picture                                    */
+    int32_t  reserved[4];
+} p264b200_synth_cfg;
+
+void p264b200_synth_default(p264b200_synth_cfg *cfg, int mb_w, int mb_h);
+p264b200_synth *p264b200_synth_open(const p264b200_synth_cfg *cfg);
+void p264b200_synth_close(p264b200_synth *s);
+/* next picture; *out points at generator-owned buffers valid until the next call */
+int  p264b200_synth_next(p264b200_synth *s, p264b200_frame_syntax *out);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -82,6 +82,30 @@ class EngineCfg(C.Structure):
     ]
 
 
+class SynthCfg(C.Structure):
+    _fields_ = [
+        ("mb_w", C.c_int32),
+        ("mb_h", C.c_int32),
+        ("n_refs", C.c_int32),
+        ("seed", C.c_uint64),
+        ("qp_min", C.c_int32),
+        ("qp_max", C.c_int32),
+        ("qp_step", C.c_int32),
+        ("coded_pct", C.c_int32),
+        ("max_level", C.c_int32),
+        ("mv_range", C.c_int32),
+        ("sub8x8", C.c_int32),
+        ("intra_pct", C.c_int32),
+        ("skip_pct", C.c_int32),
+        ("deblock", C.c_int32),
+        ("sweep_offsets", C.c_int32),
+        ("chroma_qp_index_offset", C.c_int32),
+        ("confine_mv", C.c_int32),
+        ("first_intra", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
 class P264Error(RuntimeError):
     pass
 
@@ -126,6 +150,10 @@ def load_library() -> C.CDLL:
         "p264b200_annexb_next": (i32, [u8p, C.c_size_t] + [C.POINTER(C.c_size_t)] * 3),
         "p264b200_nal_unescape": (i32, [u8p, i32, u8p, C.POINTER(i32), C.POINTER(i32)]),
         "p264b200_cavlc_table_entry": (i32, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "p264b200_synth_default": (None, [C.POINTER(SynthCfg), i32, i32]),
+        "p264b200_synth_open": (vp, [C.POINTER(SynthCfg)]),
+        "p264b200_synth_close": (None, [vp]),
+        "p264b200_synth_next": (i32, [vp, C.POINTER(FrameSyntax)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -221,6 +249,51 @@ class Parser:
             fs = self.nal(ty, ri, payload)
             if fs is not None:
                 yield Frame.from_syntax(fs)
+
+
+class Synth:
+    """Synthetic P-frame stream generator (BASELINE.json configs 3-5); see csrc/host/synth.cc."""
+
+    def __init__(self, mb_w, mb_h, **kw):
+        self._lib = load_library()
+        self.cfg = SynthCfg()
+        self._lib.p264b200_synth_default(C.byref(self.cfg), mb_w, mb_h)
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError(f"unknown synth option {k}")
+            setattr(self.cfg, k, v)
+        self._s = self._lib.p264b200_synth_open(C.byref(self.cfg))
+        if not self._s:
+            raise P264Error("p264b200_synth_open: bad configuration")
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.p264b200_synth_close(self._s)
+            self._s = None
+
+    __del__ = close
+
+    def next_syntax(self) -> FrameSyntax:
+        """Next picture, pointing at generator-owned memory (valid until the next call)."""
+        fs = FrameSyntax()
+        _check(self._lib.p264b200_synth_next(self._s, C.byref(fs)), "p264b200_synth_next")
+        return fs
+
+    def next(self) -> Frame:
+        return Frame.from_syntax(self.next_syntax())
+
+
+def smooth_picture(width, height, seed=0):
+    """Bounded smooth I420 test picture (samples in [64,192]) used to seed reference slots: keeps the
+    reference's mc_hc inside its 416-entry clip table (core/clip1.h:25-36)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    ph = rng.uniform(0, 6.28, 6)
+    fx, fy = rng.uniform(0.01, 0.06, 3), rng.uniform(0.01, 0.06, 3)
+    img = 128 + 24 * np.sin(fx[0] * xx + ph[0]) + 20 * np.sin(fy[0] * yy + ph[1]) + 16 * np.sin(fx[1] * xx + fy[1] * yy + ph[2])
+    y = np.clip(img + rng.integers(-3, 4, img.shape), 64, 192).astype(np.uint8)
+    c = lambda a, b: np.clip(128 + 30 * np.sin(fx[2] * xx[::2, ::2] * a + fy[2] * yy[::2, ::2] * b + ph[3]) + rng.integers(-2, 3, (height // 2, width // 2)), 64, 192).astype(np.uint8)
+    return y, c(1.0, 0.5), c(0.4, 1.2)
 
 
 class Engine:

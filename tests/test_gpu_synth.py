@@ -1,0 +1,78 @@
+"""GPU: configs 3/4/5 of BASELINE.json at parity-test sizes -- synthetic P streams (all partition
+shapes, all 16 quarter-pel phases, QP sweep, multi-reference, deblock offsets, intra MBs) through
+the C-ABI engine, byte-compared with the CPU oracle picture by picture."""
+import numpy as np
+import pytest
+
+import p264decoder_b200 as P
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(got, want, fr, what):
+    for name, g, w, s in zip("YUV", got, want, (16, 8, 8)):
+        bad = np.argwhere(g != w)
+        if len(bad):
+            mbs = sorted({(int(r) // s, int(c) // s) for r, c in bad})[:6]
+            kinds = [(my, mx, int(fr.mbs["mb_type"][my * fr.hdr.mb_w + mx])) for my, mx in mbs]
+            raise AssertionError(f"{what} plane {name}: {len(bad)} samples differ; first MBs (y,x,type) {kinds}")
+
+
+def _run_stream(mb_w, mb_h, n_frames, lanes=1, **kw):
+    n_slots = kw.get("n_refs", 1) + 1
+    eng = P.Engine(mb_w, mb_h, n_slots=n_slots, lanes=lanes)
+    syns = [P.Synth(mb_w, mb_h, **dict(kw, seed=kw.get("seed", 7) + 101 * l)) for l in range(lanes)]
+    rings = [O.OracleFrames(mb_w, mb_h, n_slots) for _ in range(lanes)]
+    if not kw.get("first_intra", 1):
+        for l in range(lanes):
+            for s in range(n_slots):
+                pic = P.smooth_picture(16 * mb_w, 16 * mb_h, seed=l * 10 + s)
+                eng.upload(l, s, *pic)
+                rings[l].set(s, *pic)
+    for i in range(n_frames):
+        frames = [s.next() for s in syns]
+        for l, fr in enumerate(frames):
+            eng.stage(0, l, fr.syntax())
+        eng.recon_step(0, lanes)
+        eng.sync()
+        for l, fr in enumerate(frames):
+            want = rings[l].recon(fr)
+            got = eng.download(l, fr.hdr.dst_slot)
+            _compare(got, want, fr, f"picture {i} lane {l}")
+    eng.close()
+
+
+def test_small_all_features():
+    _run_stream(8, 6, 8, n_refs=1, seed=1, intra_pct=10, sweep_offsets=1)
+
+
+def test_multi_ref_chroma_offset():
+    _run_stream(11, 9, 8, n_refs=4, seed=3, intra_pct=5, sweep_offsets=1, chroma_qp_index_offset=-3)
+
+
+def test_full_qp_range_and_big_levels():
+    # exercises the int16 wrap-around points of dequant / IDCT (levels far beyond real streams)
+    _run_stream(6, 5, 10, n_refs=2, seed=4, intra_pct=30, max_level=2000, qp_min=0, qp_max=51, qp_step=3, coded_pct=60)
+
+
+def test_unconfined_mvs_far_outside_picture():
+    # MVs up to +-200 samples: beyond the reference's 32-sample border (undefined there); the engine
+    # and the oracle both implement the standard's unrestricted-MV replication
+    _run_stream(5, 4, 6, n_refs=1, seed=5, mv_range=200, confine_mv=0, first_intra=0)
+
+
+def test_no_deblock_and_no_residual():
+    _run_stream(7, 5, 4, n_refs=1, seed=6, deblock=0, coded_pct=0, skip_pct=50)
+
+
+def test_lanes_batched():
+    _run_stream(9, 7, 5, lanes=5, n_refs=2, seed=11, intra_pct=8)
+
+
+def test_1080p_stream():
+    _run_stream(120, 68, 3, n_refs=1, seed=264, intra_pct=2)
+
+
+def test_4k_multiref_two_pictures():
+    _run_stream(240, 135, 2, n_refs=4, seed=2160, sweep_offsets=1, first_intra=0)
