@@ -308,3 +308,19 @@ API void ref_dequant_2x2_dc(int16_t d[4], int qp)
     if (!f) f = ref_feed_open(1, 1, 2);
     p264_mb_dequant_2x2_dc((int16_t(*)[2])d, f->h->dequant4_mf[CQM_4IC], qp);
 }
+
+/* mc_luma / mc_chroma of the reference on a frame slot prepared by ref_feed_write (integer plane +
+ * the three half-pel planes of p264_frame_filter), block at picture position (bx,by) */
+API void ref_mc_luma(ref_feed *f, int slot, int bx, int by, int mvx, int mvy, int w, int h, uint8_t *dst, int dstride)
+{
+    p264_frame_t *fr = f->slot[slot];
+    uint8_t *src[4];
+    int i;
+    for (i = 0; i < 4; i++) src[i] = fr->filtered[i] + by * fr->i_stride[0] + bx;
+    f->h->mc.mc_luma(src, fr->i_stride[0], dst, dstride, mvx, mvy, w, h);
+}
+API void ref_mc_chroma(ref_feed *f, int slot, int plane, int bx, int by, int mvx, int mvy, int w, int h, uint8_t *dst, int dstride)
+{
+    p264_frame_t *fr = f->slot[slot];
+    f->h->mc.mc_chroma(fr->plane[plane] + by * fr->i_stride[plane] + bx, fr->i_stride[plane], dst, dstride, mvx, mvy, w, h);
+}

@@ -36,6 +36,7 @@ __device__ __forceinline__ void border_plane_word(uint8_t *plane, int stride, in
 
 __device__ __forceinline__ int border_words(int W, int H, int pad) { return 2 * pad * ((W + 2 * pad) >> 2) + H * (pad >> 1); }
 
+#ifdef P264B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(256) border_kernel(const FrameDesc *__restrict__ descs, Geometry g, uint8_t *y,
                                                      uint8_t *u, uint8_t *v)
 {
@@ -54,5 +55,7 @@ __global__ void __launch_bounds__(256) border_kernel(const FrameDesc *__restrict
     else if (idx < ny + 2 * nc)
         border_plane_word(pl[2], g.c_stride, g.width / 2, g.height / 2, kChromaPad, idx - ny - nc);
 }
+
+#endif  // P264B200_DEFINE_KERNELS
 
 }  // namespace p264b200

@@ -31,18 +31,18 @@ struct FrameDesc {
 };
 
 // ---- tables (core/set.c:27-35, core/macroblock.h:210-218, core/frame.c:262-291) -------------
-__constant__ uint8_t c_dq_scale[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20},
+static __constant__ uint8_t c_dq_scale[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20},
                                          {14, 18, 23}, {16, 20, 25}, {18, 23, 29}};
-__constant__ uint8_t c_chroma_qp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
+static __constant__ uint8_t c_chroma_qp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
                                         18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
                                         34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
-__constant__ uint8_t c_alpha[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,   0,   0,   4,   4,
+static __constant__ uint8_t c_alpha[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,   0,   0,   4,   4,
                                     5,  6,  7,  8,  9,  10, 12, 13, 15, 17, 20, 22, 25, 28,  32,  36,  40,  45,
                                     50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
-__constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  0,  0,  0,  0,  0,  2,  2,
+static __constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  0,  0,  0,  0,  0,  2,  2,
                                    2, 3, 3, 3, 3, 4, 4, 4, 6,  6,  7,  7,  8,  8,  9,  9,  10, 10,
                                    11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
-__constant__ uint8_t c_tc0[52][4] = {
+static __constant__ uint8_t c_tc0[52][4] = {
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 1, 0},   {0, 0, 1, 0},   {0, 0, 1, 0},   {0, 0, 1, 0},
@@ -52,7 +52,7 @@ __constant__ uint8_t c_tc0[52][4] = {
     {4, 6, 9, 0},  {5, 7, 10, 0}, {6, 8, 11, 0}, {6, 8, 13, 0},  {7, 10, 14, 0}, {8, 11, 16, 0}, {9, 12, 18, 0},
     {10, 13, 20, 0}, {11, 15, 23, 0}, {13, 17, 25, 0}};
 // zig-zag scan position -> raster index 4*y+x (decoder/macroblock.c:602-603)
-__constant__ uint8_t c_zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+static __constant__ uint8_t c_zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
 
 __device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip8i(int v) { return min(max(v, 0), 255); }

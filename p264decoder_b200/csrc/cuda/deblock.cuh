@@ -197,6 +197,7 @@ __device__ __forceinline__ void deblock_mb(DeblockSmem &s, const FrameDesc &fd, 
     }
 }
 
+#ifdef P264B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(32) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int *ticket)
 {
     __shared__ DeblockSmem s;
@@ -224,5 +225,7 @@ __global__ void __launch_bounds__(32) deblock_kernel(const FrameDesc *__restrict
         if (lane == 0) st_release(prog + row, mbx + 1);
     }
 }
+
+#endif  // P264B200_DEFINE_KERNELS
 
 }  // namespace p264b200

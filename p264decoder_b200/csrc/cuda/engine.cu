@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#define P264B200_DEFINE_KERNELS 1
 #include "border.cuh"
 #include "common.cuh"
 #include "deblock.cuh"

@@ -133,6 +133,7 @@ __device__ __forceinline__ void mc_chroma_2x2(const uint8_t *__restrict__ src, i
             o[r * 2 + c] = (cA * p[r][c] + cB * p[r][c + 1] + cC * p[r + 1][c] + cD * p[r + 1][c + 1] + 32) >> 6;
 }
 
+#ifdef P264B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(kInterThreads) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g)
 {
     const FrameDesc &fd = descs[blockIdx.y];
@@ -196,5 +197,7 @@ __global__ void __launch_bounds__(kInterThreads) recon_inter_kernel(const FrameD
         for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(dst + r * g.c_stride) = px[r];
     }
 }
+
+#endif  // P264B200_DEFINE_KERNELS
 
 }  // namespace p264b200

@@ -101,7 +101,7 @@ __device__ __forceinline__ void plane_params(const uint8_t *tile, int ts, int &i
     }
 }
 
-__device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const Geometry &g, const p264b200_mb &m, int mbx,
+static __device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const Geometry &g, const p264b200_mb &m, int mbx,
                                int mby, int lane)
 {
     const bool has_left = mbx > 0, has_top = mby > 0;
@@ -304,6 +304,7 @@ __device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const Geometry
     }
 }
 
+#ifdef P264B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__restrict__ descs, Geometry g, int *ticket)
 {
     __shared__ IntraSmem s;
@@ -340,5 +341,7 @@ __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__rest
     __syncwarp();
     if (lane == 0) st_release(prog + row, g.mb_w);
 }
+
+#endif  // P264B200_DEFINE_KERNELS
 
 }  // namespace p264b200

@@ -1,0 +1,128 @@
+"""CPU: host-side logic -- CAVLC code tables against the standard's tables (golden parsed from the
+reference's core/vlc.h), Annex-B splitting and emulation-prevention removal against the
+reference's own p264_nal_decode, parser error behaviour, synthetic generator invariants."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import p264decoder_b200 as P
+import _oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_cavlc_tables_match_standard():
+    lib = P.load_library()
+    gold = json.loads((ROOT / "tests" / "golden" / "cavlc_tables.json").read_text())
+
+    def entry(kind, table, sym):
+        l, b = C.c_int(), C.c_int()
+        assert lib.p264b200_cavlc_table_entry(kind, table, sym, C.byref(l), C.byref(b)) == 0
+        return [b.value, l.value]
+
+    for t in range(4):
+        for s in range(68):
+            if (s & 3) <= (s >> 2):
+                assert entry(0, t, s) == gold["coeff_token"][t][s], (t, s)
+    for s in range(20):
+        if (s & 3) <= (s >> 2):
+            assert entry(1, 0, s) == gold["coeff_token"][4][s], s
+    for t in range(15):
+        for s in range(16 - t):
+            assert entry(2, t, s) == gold["total_zeros"][t][s], (t, s)
+    for t in range(3):
+        for s in range(4 - t):
+            assert entry(3, t, s) == gold["total_zeros_dc"][t][s], (t, s)
+    for t in range(7):
+        for s in range([2, 3, 4, 5, 6, 7, 15][t]):
+            assert entry(4, t, s) == gold["run_before"][t][s], (t, s)
+
+
+def test_annexb_split_and_unescape():
+    raw = bytes([0, 0, 0, 1, 0x67, 1, 2, 0, 0, 3, 1, 9, 0, 0, 1, 0x68, 5, 0, 0, 3, 0, 0, 0, 0, 1, 0x65, 7, 0, 0, 3])
+    nals = list(P.split_annexb(np.frombuffer(raw, np.uint8)))
+    assert [(t, r) for t, r, _ in nals] == [(7, 3), (8, 3), (5, 3)]
+    assert nals[0][2].tolist() == [1, 2, 0, 0, 1, 9]
+    # every zero in front of the next 01 belongs to its start code (p264decoder.c:259-301), and the
+    # reference only unescapes while src < end-3 (core/core.c:317): the trailing 00 00 03 survives
+    assert nals[1][2].tolist() == [5, 0, 0, 3]
+    assert nals[2][2].tolist() == [7, 0, 0, 3]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="needs oracle/_ref")
+def test_nal_decode_equals_reference():
+    ref = O.ref()
+
+    class Nal(C.Structure):
+        _fields_ = [("i_ref_idc", C.c_int), ("i_type", C.c_int), ("i_payload", C.c_int), ("p_payload", C.c_void_p)]
+
+    rng = np.random.default_rng(5)
+    lib = P.load_library()
+    for n in [1, 2, 3, 4, 5, 9, 64, 1000]:
+        for _ in range(20):
+            data = rng.choice(np.array([0, 0, 0, 3, 1, 7], np.uint8), size=n).astype(np.uint8)
+            buf_r, buf_o = np.zeros(n + 8, np.uint8), np.zeros(n + 8, np.uint8)
+            nal = Nal(0, 0, 0, buf_r.ctypes.data)
+            ref.p264_nal_decode(C.byref(nal), data.ctypes.data, n)
+            ty, ri = C.c_int(), C.c_int()
+            m = lib.p264b200_nal_unescape(data.ctypes.data, n, buf_o.ctypes.data, C.byref(ty), C.byref(ri))
+            assert (m, ty.value, ri.value) == (nal.i_payload, nal.i_type, nal.i_ref_idc)
+            assert np.array_equal(buf_r[:m], buf_o[:m])
+
+
+def test_parser_rejects_garbage_without_crashing():
+    p = P.Parser()
+    rng = np.random.default_rng(1)
+    # slice before any parameter set
+    with pytest.raises(P.P264Error):
+        p.nal(5, 3, rng.integers(0, 256, 100, dtype=np.uint8))
+    assert p.nal(6, 0, np.zeros(4, np.uint8)) is None  # SEI ignored
+    with pytest.raises(P.P264Error):
+        p.nal(2, 0, np.zeros(4, np.uint8))  # data partitioning unsupported (decoder/decoder.c:790-795)
+    for _ in range(50):
+        try:
+            p.nal(int(rng.integers(1, 9)), 3, rng.integers(0, 256, int(rng.integers(0, 60)), dtype=np.uint8))
+        except P.P264Error:
+            pass
+
+
+def test_synth_stream_invariants():
+    syn = P.Synth(9, 7, n_refs=3, seed=9, intra_pct=10)
+    last_qp = None
+    for i in range(6):
+        fr = syn.next()
+        h, m = fr.hdr, fr.mbs
+        assert (h.mb_w, h.mb_h) == (9, 7) and h.dst_slot == i % 4
+        assert h.slice_type == (P.SLICE_I if i == 0 else P.SLICE_P)
+        assert h.num_ref == min(i, 3)
+        assert sorted({h.ref_slot[k] for k in range(h.num_ref)} | {h.dst_slot}) == sorted({(i - k) % 4 for k in range(h.num_ref + 1)})
+        intra = m["mb_type"] <= P.MB_I16x16
+        assert intra.sum() == h.n_intra
+        assert (m["ref"][intra] == -1).all() and (m["mv"][intra] == 0).all()
+        assert (m["ref"][~intra] >= 0).all() and (m["ref"][~intra] < max(h.num_ref, 1)).all()
+        assert (m["coef_off"] % 8 == 0).all() and h.n_coef % 8 == 0
+        # qp_dbf follows the reference's last-QP rule
+        for mb in m:
+            coded = mb["mb_type"] == P.MB_I16x16 or mb["luma_mask"] or mb["cbp_chroma"]
+            if not coded and last_qp is not None:
+                assert mb["qp_dbf"] == last_qp
+            elif coded:
+                assert mb["qp_dbf"] == mb["qp"]
+            last_qp = int(mb["qp_dbf"])
+    # determinism
+    a, b = P.Synth(5, 4, seed=3), P.Synth(5, 4, seed=3)
+    for _ in range(3):
+        fa, fb = a.next(), b.next()
+        assert fa.mbs.tobytes() == fb.mbs.tobytes() and fa.coefs.tobytes() == fb.coefs.tobytes()
+
+
+def test_empty_and_tiny_pictures_through_oracle():
+    # 1x1 macroblock pictures: every neighbour unavailable
+    syn = P.Synth(1, 1, n_refs=1, seed=2, intra_pct=50)
+    ring = O.OracleFrames(1, 1, 2)
+    for _ in range(5):
+        y, u, v = ring.recon(syn.next())
+        assert y.shape == (16, 16)
