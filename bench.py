@@ -56,7 +56,7 @@ def parse_args():
 
 
 def synth_kwargs(args, lane, rank):
-    return dict(n_refs=args.refs, seed=264 + 1000 * rank + lane, first_intra=0, confine_mv=1, intra_pct=0,
+    return dict(n_refs=args.refs, seed=stream_seed(rank, lane), first_intra=0, confine_mv=1, intra_pct=0,
                 coded_pct=25, max_level=8, mv_range=16, sub8x8=1, skip_pct=5, qp_min=20, qp_max=40, qp_step=2)
 
 
@@ -178,6 +178,27 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def stream_seed(rank, lane):
+    """Streams are disjoint across ranks and lanes: global stream id = rank * 1000 + lane (replicas only)."""
+    return 264 + 1000 * rank + lane
+
+
+def reduce_max(values, dist, device=None):
+    """max over ranks of a list of floats (timing is the slowest rank's); identity without a process group"""
+    if dist is None:
+        return list(values)
+    import torch
+
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def aggregate_value(world, lanes, ms_step):
+    """whole-job pictures/s: every rank reconstructs `lanes` pictures per step (weak scaling)"""
+    return world * lanes / (ms_step / 1000.0)
 
 
 def workload_config(args, lanes):
@@ -319,19 +340,14 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- max over ranks
     ms_step = ms / args.steps
-    if dist:
-        import torch
-
-        tt = torch.tensor([ms_step, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step, e2e_max = tt[0].item(), tt[1].item()
-        e2e_ms = e2e_max if e2e_ms is not None else None
+    ms_step, e2e_max = reduce_max([ms_step, e2e_ms or 0.0], dist, "cuda")
+    e2e_ms = e2e_max if e2e_ms is not None else None
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    value = world * L / (ms_step / 1000.0)
+    value = aggregate_value(world, L, ms_step)
     unit = f"{args.size}_frames/s"
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
@@ -375,7 +391,7 @@ def run_b200(args, rank, world, local_rank):
         "roofline": roofline, "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks,
     }
     if e2e_ms is not None:
-        line["e2e"] = {"value": world * L / (e2e_ms / 1000.0), "unit": unit, "h2d_bytes_per_step": int(h2d_per_step),
+        line["e2e"] = {"value": aggregate_value(world, L, e2e_ms), "unit": unit, "h2d_bytes_per_step": int(h2d_per_step),
                        "d2h_bytes_per_step": int(d2h_per_step), "ms_per_step": e2e_ms}
     if not args.no_cpu:
         cores = os.cpu_count() or 1

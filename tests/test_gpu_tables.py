@@ -126,8 +126,6 @@ def test_predict_tables(libs):
 
 def test_deblock_tables(libs):
     ours, ref = libs
-    to, tr = table(ours, "p264_deblock_init", 8), table(ref, "p264_deblock_init", 8)
-    # hmm: p264_deblock_init(cpu, pf)
     to, tr = table(ours, "p264_deblock_init", 8, 0), table(ref, "p264_deblock_init", 8, 0)
     rng = np.random.default_rng(4)
     for it in range(40):
