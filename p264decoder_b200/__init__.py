@@ -353,7 +353,7 @@ class Engine:
     def profile_read(self):
         ms, n = (C.c_float * 8)(), (C.c_uint64 * 8)()
         _check(self._lib.p264b200_profile_read(self._e, C.byref(ms), C.byref(n)), "p264b200_profile_read")
-        names = ["recon_inter", "recon_intra", "deblock", "border"]
+        names = ["recon_inter", "recon_intra", "deblock", "border", "deblock_bs"]
         return {k: (ms[i], n[i]) for i, k in enumerate(names)}
 
     @property

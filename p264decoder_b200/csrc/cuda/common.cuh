@@ -26,7 +26,9 @@ struct FrameDesc {
     const int16_t *coefs;
     uint8_t *cur[3];                    // plane origins (sample 0,0) of the picture being reconstructed
     const uint8_t *ref[kMaxRefs][3];    // list-0 reference plane origins
-    int *row_progress;                  // [2][mb_h]: intra wavefront, deblock wavefront
+    int *row_progress;                  // [3][mb_h]: intra, luma deblock, chroma deblock wavefronts
+    struct DeblockSide *dbf_bs;         // per-MB boundary strengths (deblock_bs_kernel -> deblock_kernel)
+    uint32_t *dbf_qp;                   // per-MB qp | qp_left << 8 | qp_top << 16
     int slice_type, deblock, alpha_off, beta_off, chroma_qp_off, n_intra, num_ref, pad_;
 };
 
@@ -42,7 +44,7 @@ static __constant__ uint8_t c_alpha[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0
 static __constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  0,  0,  0,  0,  0,  2,  2,
                                    2, 3, 3, 3, 3, 4, 4, 4, 6,  6,  7,  7,  8,  8,  9,  9,  10, 10,
                                    11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
-static __constant__ uint8_t c_tc0[52][4] = {
+static __constant__ __align__(16) uint8_t c_tc0[52][4] = {
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},   {0, 0, 0, 0},
     {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 0, 0},  {0, 0, 1, 0},   {0, 0, 1, 0},   {0, 0, 1, 0},   {0, 0, 1, 0},

@@ -35,7 +35,7 @@ void set_err(const char *what, cudaError_t e)
         }                                         \
     } while (0)
 
-enum { K_INTER = 0, K_INTRA, K_DEBLOCK, K_BORDER, K_COUNT };
+enum { K_INTER = 0, K_INTRA, K_DEBLOCK, K_BORDER, K_DEBLOCK_BS, K_COUNT };
 }  // namespace
 
 struct p264b200_engine {
@@ -49,7 +49,9 @@ struct p264b200_engine {
     int16_t *d_coefs = nullptr;
     FrameDesc *d_descs = nullptr, *h_descs = nullptr;
     size_t coef_cap = 0;  // int16 per lane per step
-    int *d_sync = nullptr;  // [4 tickets/pad][lanes][2*mb_h]
+    DeblockSide *d_bs = nullptr;   // [lanes][n_mb]
+    uint32_t *d_dqp = nullptr;     // [lanes][n_mb]
+    int *d_sync = nullptr;  // [4 tickets/pad][lanes][3*mb_h]: intra, luma deblock, chroma deblock wavefronts
     size_t sync_bytes = 0;
     std::vector<uint8_t> slot_flags;  // [step][lane]: bit0 intra MBs present, bit1 deblock on, bit2 P slice
     // timing
@@ -58,9 +60,10 @@ struct p264b200_engine {
     std::vector<cudaEvent_t> prof_ev;   // pairs
     std::vector<int> prof_kind;
     size_t prof_used = 0;
-    float prof_ms[K_COUNT] = {0, 0, 0, 0};
-    uint64_t prof_n[K_COUNT] = {0, 0, 0, 0};
+    float prof_ms[K_COUNT] = {0, 0, 0, 0, 0};
+    uint64_t prof_n[K_COUNT] = {0, 0, 0, 0, 0};
     uint64_t launches = 0;
+    int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
 
     uint8_t *plane(int lane, int slot, int c) const
     {
@@ -154,6 +157,8 @@ void p264b200_engine_destroy(p264b200_engine *e)
     cudaFree(e->d_coefs);
     cudaFree(e->d_descs);
     cudaFree(e->d_sync);
+    cudaFree(e->d_bs);
+    cudaFree(e->d_dqp);
     if (e->h_descs) cudaFreeHost(e->h_descs);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -177,6 +182,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     p264b200_engine *e = new (std::nothrow) p264b200_engine;
     if (!e) return P264B200_ENOMEM;
     e->cfg = *cfg;
+    if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
     Geometry &g = e->g;
     g.mb_w = cfg->mb_w;
     g.mb_h = cfg->mb_h;
@@ -193,7 +199,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     e->coef_cap = (e->coef_cap + 7) & ~(size_t)7;
     const size_t frames = (size_t)cfg->lanes * cfg->n_slots;
     const size_t slots = (size_t)cfg->stage_steps * cfg->lanes;
-    e->sync_bytes = (4 + (size_t)cfg->lanes * 2 * g.mb_h) * sizeof(int);
+    e->sync_bytes = (4 + (size_t)cfg->lanes * 3 * g.mb_h) * sizeof(int);
     int rc = P264B200_OK;
     auto fail = [&](const char *what, cudaError_t err) {
         set_err(what, err);
@@ -208,6 +214,8 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaMalloc(&e->d_descs, slots * sizeof(FrameDesc))) != cudaSuccess) fail("cudaMalloc descs", err);
     if (!rc && (err = cudaMallocHost(&e->h_descs, slots * sizeof(FrameDesc))) != cudaSuccess) fail("cudaMallocHost descs", err);
     if (!rc && (err = cudaMalloc(&e->d_sync, e->sync_bytes)) != cudaSuccess) fail("cudaMalloc sync", err);
+    if (!rc && (err = cudaMalloc(&e->d_bs, (size_t)cfg->lanes * n_mb * sizeof(DeblockSide))) != cudaSuccess) fail("cudaMalloc bs", err);
+    if (!rc && (err = cudaMalloc(&e->d_dqp, (size_t)cfg->lanes * n_mb * sizeof(uint32_t))) != cudaSuccess) fail("cudaMalloc dqp", err);
     if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
     if (!rc) {
@@ -265,7 +273,9 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     for (int c = 0; c < 3; c++) d.cur[c] = e->plane(lane, h.dst_slot, c);
     for (int i = 0; i < h.num_ref; i++)
         for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
-    d.row_progress = e->d_sync + 4 + (size_t)lane * 2 * g.mb_h;
+    d.row_progress = e->d_sync + 4 + (size_t)lane * 3 * g.mb_h;
+    d.dbf_bs = e->d_bs + (size_t)lane * n_mb;
+    d.dbf_qp = e->d_dqp + (size_t)lane * n_mb;
     d.slice_type = h.slice_type;
     d.deblock = h.deblock;
     d.alpha_off = h.alpha_c0_offset;
@@ -299,8 +309,12 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         recon_intra_kernel<<<g.mb_h * n_lanes, 32, 0, e->stream>>>(descs, g, e->d_sync + 0);
     }
     if (dbf) {
+        {
+            ProfScope p(e, K_DEBLOCK_BS);
+            deblock_bs_kernel<<<dim3((4 * n_mb + 255) / 256, n_lanes), 256, 0, e->stream>>>(descs, g);
+        }
         ProfScope p(e, K_DEBLOCK);
-        deblock_kernel<<<g.mb_h * n_lanes, 32, 0, e->stream>>>(descs, g, e->d_sync + 1);
+        deblock_kernel<<<2 * ((n_lanes + 1) / 2) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfRows, 0, e->stream>>>(descs, g, n_lanes, e->d_sync + 1, e->dbg);
     }
     {
         ProfScope p(e, K_BORDER);
