@@ -59,6 +59,17 @@ static __constant__ uint8_t c_zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7
 __device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip8i(int v) { return min(max(v, 0), 255); }
 
+// clamp four ints to 0..255 and pack them, v0 in the low byte: two I2IP (cvt.pack.sat) instructions
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
+{
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+}
+// per-byte rounded average (a + b + 1) >> 1 of four packed u8
+__device__ __forceinline__ uint32_t avg4_u8(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }
+
 __device__ __forceinline__ int mb_ref8(const p264b200_mb &m, int b) { return m.ref[(b >> 3) * 2 + ((b & 3) >> 1)]; }
 
 // ------------------------------------------------------------------ coefficient path
@@ -116,12 +127,9 @@ __device__ __forceinline__ void idct4x4_add(const int d[16], uint32_t px[4])
     int r[16];
     idct4x4_core(d, r);
 #pragma unroll
-    for (int y = 0; y < 4; y++) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int x = 0; x < 4; x++) o |= (uint32_t)clip8i((int)((px[y] >> (8 * x)) & 0xff) + r[y * 4 + x]) << (8 * x);
-        px[y] = o;
-    }
+    for (int y = 0; y < 4; y++)
+        px[y] = pack4_sat_u8((int)(px[y] & 0xff) + r[y * 4 + 0], (int)((px[y] >> 8) & 0xff) + r[y * 4 + 1],
+                             (int)((px[y] >> 16) & 0xff) + r[y * 4 + 2], (int)(px[y] >> 24) + r[y * 4 + 3]);
 }
 
 // chroma DC: dct2x2dc (core/dct.c:55-68) then p264_mb_dequant_2x2_dc (core/quant.c:138-159)
