@@ -128,6 +128,49 @@ __device__ __forceinline__ void chroma_edge(int p1, int &p0, int &q0, int q1, in
     q0 = f ? m0 : q0;
 }
 
+// packed-parameter variants (see DeblockSide)
+__device__ __forceinline__ void luma_edge_p(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3, int bs,
+                                            uint32_t prm, bool any_strong)
+{
+    const int alpha = prm & 0xff, beta = (prm >> 8) & 31;
+    const int tc0 = (int)((prm >> (8 + 5 * bs)) & 31) & (bs < 4 ? 31 : 0);
+    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
+    const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+    const bool fn = f && bs < 4;
+    const int avg = (p0 + q0 + 1) >> 1;
+    const int np1 = p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0);
+    const int nq1 = q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0);
+    const int tc = tc0 + (int)ap + (int)aq;
+    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+    int r1 = (fn && ap) ? np1 : p1, r0 = fn ? clip8i(p0 + delta) : p0;
+    int s0 = fn ? clip8i(q0 - delta) : q0, s1 = (fn && aq) ? nq1 : q1;
+    int r2 = p2, s2 = q2;
+    if (any_strong) {  // warp-uniform: some line of this edge is an intra macroblock edge
+        const bool fs = f && bs == 4;
+        const bool sm = abs(p0 - q0) < ((alpha >> 2) + 2);
+        const bool sp = fs && sm && ap, sq = fs && sm && aq;
+        const int wp0 = (2 * p1 + p0 + q1 + 2) >> 2, wq0 = (2 * q1 + q0 + p1 + 2) >> 2;
+        r0 = fs ? (sp ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : wp0) : r0;
+        r1 = sp ? (p2 + p1 + p0 + q0 + 2) >> 2 : r1;
+        r2 = sp ? (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3 : r2;
+        s0 = fs ? (sq ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : wq0) : s0;
+        s1 = sq ? (p0 + q0 + q1 + q2 + 2) >> 2 : s1;
+        s2 = sq ? (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3 : s2;
+    }
+    p2 = r2, p1 = r1, p0 = r0, q0 = s0, q1 = s1, q2 = s2;
+}
+__device__ __forceinline__ void chroma_edge_p(int p1, int &p0, int &q0, int q1, int bs, uint32_t prm)
+{
+    const int alpha = prm & 0xff, beta = (prm >> 8) & 31;
+    const int tc = (int)((prm >> (8 + 5 * bs)) & 31) + 1;
+    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
+    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+    const int n0 = bs < 4 ? clip8i(p0 + delta) : (2 * p1 + p0 + q1 + 2) >> 2;
+    const int m0 = bs < 4 ? clip8i(q0 - delta) : (2 * q1 + q0 + p1 + 2) >> 2;
+    p0 = f ? n0 : p0;
+    q0 = f ? m0 : q0;
+}
+
 // alpha / beta / packed tc0[3] for an averaged QP (core/frame.c:476-483)
 struct EdgeParams {
     int alpha, beta;
@@ -167,9 +210,20 @@ __device__ __forceinline__ int boundary_strength(const p264b200_mb *__restrict__
 // segment seg) << 4; plus one word qp | qp_left << 8 | qp_top << 16 (the QPs the deblocker sees).
 // A luma thread (line i) and a chroma thread (line l) each need exactly one bS word:
 // seg = i >> 2 resp. l >> 1, for both edge directions.
+// The same pre-pass also resolves the filter parameters (core/frame.c:476-483) of the three edge kinds a
+// macroblock has -- left MB edge, top MB edge, inner edges -- for luma and chroma:
+//   bits 0-7 alpha, 8-12 beta, 13-17 / 18-22 / 23-27 tc0[bS-1] for bS = 1..3
 struct DeblockSide {
     uint32_t bs[4];
+    uint32_t luma[4];    // [left, top, inner, unused]
+    uint32_t chroma[4];
 };
+__device__ __forceinline__ uint32_t pack_edge_params(int qp, int alpha_off, int beta_off)
+{
+    const int ia = clip3i(qp + alpha_off, 0, 51);
+    return (uint32_t)c_alpha[ia] | ((uint32_t)c_beta[clip3i(qp + beta_off, 0, 51)] << 8) | ((uint32_t)c_tc0[ia][0] << 13) |
+           ((uint32_t)c_tc0[ia][1] << 18) | ((uint32_t)c_tc0[ia][2] << 23);
+}
 
 constexpr int kLS = 20;                  // luma transpose tile: 20 rows (-4..15) x 16 cols, 20-byte rows
 constexpr int kLHalf = 20 * kLS + 16;    // bytes per stream half (+16 shifts the second half's banks)
@@ -198,9 +252,13 @@ __global__ void __launch_bounds__(256) deblock_bs_kernel(const FrameDesc *__rest
         w |= (uint32_t)(bv | (bh << 4)) << (8 * e);
     }
     fd.dbf_bs[mb_xy].bs[seg] = w;
-    if (seg == 0) {
-        const int qp = m->qp_dbf, ql = mbx > 0 ? m[-1].qp_dbf : qp, qt = mby > 0 ? m[-g.mb_w].qp_dbf : qp;
-        fd.dbf_qp[mb_xy] = (uint32_t)(qp | (ql << 8) | (qt << 16));
+    if (seg < 3) {
+        // seg 0/1/2 -> left / top / inner edge parameters, luma QP average and mapped chroma QP average
+        const int qp = m->qp_dbf, qn = seg == 0 ? (mbx > 0 ? m[-1].qp_dbf : qp) : seg == 1 ? (mby > 0 ? m[-g.mb_w].qp_dbf : qp) : qp;
+        const int off = fd.chroma_qp_off;
+        const int qc = c_chroma_qp[clip3i(qp + off, 0, 51)], qcn = c_chroma_qp[clip3i(qn + off, 0, 51)];
+        fd.dbf_bs[mb_xy].luma[seg] = pack_edge_params((qp + qn + 1) >> 1, fd.alpha_off, fd.beta_off);
+        fd.dbf_bs[mb_xy].chroma[seg] = pack_edge_params((qc + qcn + 1) >> 1, fd.alpha_off, fd.beta_off);
     }
 }
 
@@ -221,15 +279,20 @@ struct DbfSmem {
 
 __device__ __forceinline__ void wait_smem(volatile int *flag, int need, int lane)
 {
-    if (lane == 0)
-        while (*flag < need) __nanosleep(16);
+    if (lane == 0) {
+        // exponential back-off: rows that have not started yet must not steal issue slots from working warps
+        int spins = 0;
+        while (*flag < need) __nanosleep(++spins < 64 ? 20 : 1000);
+    }
     __threadfence_block();
     __syncwarp();
 }
 __device__ __forceinline__ void wait_global(const int *prog, int need, bool poll)
 {
-    if (poll)
-        while (ld_acquire(prog) < need) __nanosleep(20);
+    if (poll) {
+        int spins = 0;
+        while (ld_acquire(prog) < need) __nanosleep(++spins < 32 ? 20 : 1000);
+    }
     __syncwarp();
 }
 
@@ -238,24 +301,36 @@ struct RowCtx {
     bool top_smem, top_glob, bottom_smem, bottom_glob;
 };
 
+__device__ __forceinline__ int ub(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }  // byte k, zero-extended
+__device__ __forceinline__ uint32_t pk4(int a, int b, int c, int d) { return (uint32_t)(a | (b << 8) | (c << 16) | (d << 24)); }
+
+// shared-memory progress is counted in half macroblocks: 2x+1 = vertical edges of MB x done (so the
+// previous MB's columns 12..15 are final), 2x+2 = MB x done.  Row r+1 may filter the top edge of MB x as
+// soon as row r has finished the VERTICAL edges of MB x+1 -- a lag of 1.5 instead of 2 macroblocks.
+__device__ __forceinline__ void publish_smem(volatile int *flag, int v, int lane)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *flag = v;
+}
+
 // ------------------------------------------------------------------------------ luma rows
 __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, const FrameDesc &fd, const Geometry &g, int half,
                                                  int i, bool act)
 {
     const int lane = threadIdx.x & 31, row = rc.row, w = rc.w;
     uint8_t *T = sm.tile[w] + half * kLHalf;  // this half's tile, row r at T + (r + 4) * kLS
-    int *prog = fd.row_progress + g.mb_h;     // [1]: luma deblock wavefront (CTA boundaries only)
+    int *prog = fd.row_progress + g.mb_h;     // [1]: luma deblock wavefront (CTA boundaries only, in macroblocks)
     uint8_t *grow = fd.cur[0] + (ptrdiff_t)(16 * row + i) * g.y_stride;  // this thread's sample row
     uint8_t *gtop = fd.cur[0] + (ptrdiff_t)(16 * row - 4 + (i & 3)) * g.y_stride;
-    const uint32_t *bsp = &fd.dbf_bs[(size_t)row * g.mb_w].bs[i >> 2];
-    const uint32_t *qpp = fd.dbf_qp + (size_t)row * g.mb_w;
+    const DeblockSide *side = fd.dbf_bs + (size_t)row * g.mb_w;
     uint32_t left = 0;                        // columns -4..-1 of this row (previous MB's 12..15)
-    uint4 own = make_uint4(0, 0, 0, 0);
-    uint32_t bsw = 0, qpw = 0;
+    uint4 own = make_uint4(0, 0, 0, 0), prm = make_uint4(0, 0, 0, 0);
+    uint32_t bsw = 0;
     if (act) {
         own = __ldcg(reinterpret_cast<const uint4 *>(grow));
-        bsw = __ldg(bsp);
-        qpw = __ldg(qpp);
+        bsw = __ldg(&side[0].bs[i >> 2]);
+        prm = __ldg(reinterpret_cast<const uint4 *>(side[0].luma));
     }
     const bool poll_g = act && i == 0 && rc.top_glob;
     // rows 13..15 are finished (and written) by the row below when it lives in this CTA
@@ -264,53 +339,50 @@ __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, c
     bool dirty_prev = false;  // the previous MB changed samples that are still only in `left`
 
     for (int mbx = 0; mbx < g.mb_w; mbx++) {
-        // ---- prefetch the next macroblock's row, strengths and QPs (no dependency on other rows)
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        uint32_t bsw_n = 0, qpw_n = 0;
+        // ---- prefetch the next macroblock's row, strengths and parameters (no dependency on other rows)
+        uint4 nxt = make_uint4(0, 0, 0, 0), prm_n = make_uint4(0, 0, 0, 0);
+        uint32_t bsw_n = 0;
         if (act && mbx + 1 < g.mb_w) {
             nxt = __ldcg(reinterpret_cast<const uint4 *>(grow + 16 * (mbx + 1)));
-            bsw_n = __ldg(bsp + 4 * (mbx + 1));
-            qpw_n = __ldg(qpp + mbx + 1);
+            bsw_n = __ldg(&side[mbx + 1].bs[i >> 2]);
+            prm_n = __ldg(reinterpret_cast<const uint4 *>(side[mbx + 1].luma));
         }
         const uint32_t bv = bsw & 0x0f0f0f0fu, bh = (bsw >> 4) & 0x0f0f0f0fu;  // byte e = bS of edge e
         const unsigned any_v = __ballot_sync(0xffffffffu, bv != 0), any_h = __ballot_sync(0xffffffffu, bh != 0);
-        const int qp = qpw & 0xff, qpl = (qpw >> 8) & 0xff, qpt = (qpw >> 16) & 0xff;
-        const EdgeParams pin = edge_params(qp, fd.alpha_off, fd.beta_off);
 
         // ---- vertical edges: the whole row lives in registers, independent of the row above
         int v[20];
         {
             const uint32_t wd[5] = {left, own.x, own.y, own.z, own.w};
 #pragma unroll
-            for (int k = 0; k < 20; k++) v[k] = (int)((wd[k >> 2] >> (8 * (k & 3))) & 0xff);
+            for (int k = 0; k < 20; k++) v[k] = ub(wd[k >> 2], k & 3);
         }
         if (any_v) {
-            const EdgeParams p0 = edge_params((qp + qpl + 1) >> 1, fd.alpha_off, fd.beta_off);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int bs = (bv >> (8 * e)) & 0xff;
                 const unsigned need = __ballot_sync(0xffffffffu, bs != 0);
                 if (!need) continue;
                 const unsigned strong = __ballot_sync(0xffffffffu, bs == 4);
-                const EdgeParams &p = e == 0 ? p0 : pin;
-                luma_edge(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3], v[4 * e + 4], v[4 * e + 5], v[4 * e + 6],
-                          v[4 * e + 7], bs, p.alpha, p.beta, p.tc0, strong != 0);
+                luma_edge_p(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3], v[4 * e + 4], v[4 * e + 5], v[4 * e + 6],
+                            v[4 * e + 7], bs, e == 0 ? prm.x : prm.z, strong != 0);
             }
         }
         // columns -4..-1 are final now (the previous MB's horizontal edges were filtered already)
         if (mbx > 0) {
-            const uint32_t lw = (uint32_t)(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+            const uint32_t lw = pk4(v[0], v[1], v[2], v[3]);
             if (act && mine && (dirty_prev || any_v)) __stcg(reinterpret_cast<uint32_t *>(grow + 16 * mbx - 4), lw);
             if (to_ring) reinterpret_cast<uint32_t *>(&sm.ring[w][(mbx - 1) % kDbfRing][half][i - 12])[3] = lw;
         }
+        if (rc.bottom_smem) publish_smem(&sm.progress[w], 2 * mbx + 1, lane);
         uint32_t r[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) r[k] = (uint32_t)(v[4 + 4 * k] | (v[5 + 4 * k] << 8) | (v[6 + 4 * k] << 16) | (v[7 + 4 * k] << 24));
+        for (int k = 0; k < 4; k++) r[k] = pk4(v[4 + 4 * k], v[5 + 4 * k], v[6 + 4 * k], v[7 + 4 * k]);
 
-        // ---- the rows above become readable once row-1 is two macroblocks ahead
+        // ---- the rows above become readable once row-1 has done the vertical edges of the next macroblock
         uint4 top = make_uint4(0, 0, 0, 0);
         if (rc.top_smem) {
-            wait_smem(&sm.progress[w - 1], min(mbx + 2, g.mb_w), lane);
+            wait_smem(&sm.progress[w - 1], min(2 * mbx + 3, 2 * g.mb_w), lane);
             if (i < 4) top = sm.ring[w - 1][mbx % kDbfRing][half][i];
         } else {
             wait_global(prog + row - 1, min(mbx + 2, g.mb_w), poll_g);
@@ -331,7 +403,6 @@ __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, c
             int c[20];
 #pragma unroll
             for (int k = 0; k < 20; k++) c[k] = T[k * kLS + i];
-            const EdgeParams p0 = edge_params((qp + qpt + 1) >> 1, fd.alpha_off, fd.beta_off);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int bs = (bh >> (8 * e)) & 0xff;
@@ -339,9 +410,8 @@ __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, c
                 if (e == 0) top_edge = need;
                 if (!need) continue;
                 const unsigned strong = __ballot_sync(0xffffffffu, bs == 4);
-                const EdgeParams &p = e == 0 ? p0 : pin;
-                luma_edge(c[4 * e], c[4 * e + 1], c[4 * e + 2], c[4 * e + 3], c[4 * e + 4], c[4 * e + 5], c[4 * e + 6],
-                          c[4 * e + 7], bs, p.alpha, p.beta, p.tc0, strong != 0);
+                luma_edge_p(c[4 * e], c[4 * e + 1], c[4 * e + 2], c[4 * e + 3], c[4 * e + 4], c[4 * e + 5], c[4 * e + 6],
+                            c[4 * e + 7], bs, e == 0 ? prm.y : prm.z, strong != 0);
             }
 #pragma unroll
             for (int k = 1; k < 20; k++) T[k * kLS + i] = (uint8_t)c[k];
@@ -369,7 +439,7 @@ __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, c
         }
         if (rc.bottom_smem) {
             // the consumer must have finished the macroblock that used this ring slot before
-            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], mbx - kDbfRing + 1, lane);
+            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], 2 * (mbx - kDbfRing) + 2, lane);
             if (i >= 12) {
                 uint32_t *slot = reinterpret_cast<uint32_t *>(&sm.ring[w][mbx % kDbfRing][half][i - 12]);
                 slot[0] = r[0], slot[1] = r[1], slot[2] = r[2];
@@ -379,12 +449,10 @@ __device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, c
         left = r[3];
         own = nxt;
         bsw = bsw_n;
-        qpw = qpw_n;
+        prm = prm_n;
         dirty_prev = (any_v | any_h) != 0;
         if (rc.bottom_glob) __threadfence();
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) sm.progress[w] = mbx + 1;
+        publish_smem(&sm.progress[w], 2 * mbx + 2, lane);
         if (rc.bottom_glob && act && i == 0) st_release(prog + row, mbx + 1);
     }
 }
@@ -402,59 +470,54 @@ __device__ __forceinline__ void deblock_chroma_row(DbfSmem &sm, const RowCtx rc,
     uint8_t *grow = fd.cur[1 + pl] + (ptrdiff_t)(8 * row + l) * g.c_stride;
     // threads 0..3 of a half also move the two rows above: (plane i>>1, row -2 + (i&1))
     uint8_t *gtop = fd.cur[1 + ((i >> 1) & 1)] + (ptrdiff_t)(8 * row - 2 + (i & 1)) * g.c_stride;
-    const uint32_t *bsp = &fd.dbf_bs[(size_t)row * g.mb_w].bs[l >> 1];
-    const uint32_t *qpp = fd.dbf_qp + (size_t)row * g.mb_w;
+    const DeblockSide *side = fd.dbf_bs + (size_t)row * g.mb_w;
     uint32_t left = 0;
     uint2 own = make_uint2(0, 0);
-    uint32_t bsw = 0, qpw = 0;
+    uint4 prm = make_uint4(0, 0, 0, 0);
+    uint32_t bsw = 0;
     if (act) {
         own = __ldcg(reinterpret_cast<const uint2 *>(grow));
-        bsw = __ldg(bsp);
-        qpw = __ldg(qpp);
+        bsw = __ldg(&side[0].bs[l >> 1]);
+        prm = __ldg(reinterpret_cast<const uint4 *>(side[0].chroma));
     }
     const bool poll_g = act && i == 0 && rc.top_glob;
     const bool mine = !(rc.bottom_smem && l == 7);  // row 7 is finished by the row below inside a CTA
     const bool to_ring = rc.bottom_smem && l >= 6;
-    const int off = fd.chroma_qp_off;
     bool dirty_prev = false;
 
     for (int mbx = 0; mbx < g.mb_w; mbx++) {
         uint2 nxt = make_uint2(0, 0);
-        uint32_t bsw_n = 0, qpw_n = 0;
+        uint4 prm_n = make_uint4(0, 0, 0, 0);
+        uint32_t bsw_n = 0;
         if (act && mbx + 1 < g.mb_w) {
             nxt = __ldcg(reinterpret_cast<const uint2 *>(grow + 8 * (mbx + 1)));
-            bsw_n = __ldg(bsp + 4 * (mbx + 1));
-            qpw_n = __ldg(qpp + mbx + 1);
+            bsw_n = __ldg(&side[mbx + 1].bs[l >> 1]);
+            prm_n = __ldg(reinterpret_cast<const uint4 *>(side[mbx + 1].chroma));
         }
         // only even luma edges (0 and 2) touch chroma (core/frame.c:597,620)
         const int bv0 = bsw & 0xf, bv2 = (bsw >> 16) & 0xf, bh0 = (bsw >> 4) & 0xf, bh2 = (bsw >> 20) & 0xf;
         const unsigned any_v = __ballot_sync(0xffffffffu, (bv0 | bv2) != 0), any_h = __ballot_sync(0xffffffffu, (bh0 | bh2) != 0);
-        const int qc = c_chroma_qp[clip3i((int)(qpw & 0xff) + off, 0, 51)];
-        const int qcl = c_chroma_qp[clip3i((int)((qpw >> 8) & 0xff) + off, 0, 51)];
-        const int qct = c_chroma_qp[clip3i((int)((qpw >> 16) & 0xff) + off, 0, 51)];
-        const EdgeParams pin = edge_params(qc, fd.alpha_off, fd.beta_off);
         int v[12];
         {
             const uint32_t wd[3] = {left, own.x, own.y};
 #pragma unroll
-            for (int k = 0; k < 12; k++) v[k] = (int)((wd[k >> 2] >> (8 * (k & 3))) & 0xff);
+            for (int k = 0; k < 12; k++) v[k] = ub(wd[k >> 2], k & 3);
         }
         if (any_v) {
-            const EdgeParams p0 = edge_params((qc + qcl + 1) >> 1, fd.alpha_off, fd.beta_off);
-            chroma_edge(v[2], v[3], v[4], v[5], bv0, p0.alpha, p0.beta, p0.tc0);
-            chroma_edge(v[6], v[7], v[8], v[9], bv2, pin.alpha, pin.beta, pin.tc0);
+            chroma_edge_p(v[2], v[3], v[4], v[5], bv0, prm.x);
+            chroma_edge_p(v[6], v[7], v[8], v[9], bv2, prm.z);
         }
         if (mbx > 0) {
-            const uint32_t lw = (uint32_t)(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+            const uint32_t lw = pk4(v[0], v[1], v[2], v[3]);
             if (act && mine && (dirty_prev || any_v)) __stcg(reinterpret_cast<uint32_t *>(grow + 8 * mbx - 4), lw);
             if (to_ring) sm.ring[w][(mbx - 1) % kDbfRing][half][pl * 2 + (l - 6)].y = lw;
         }
-        uint32_t r0 = (uint32_t)(v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24));
-        uint32_t r1 = (uint32_t)(v[8] | (v[9] << 8) | (v[10] << 16) | (v[11] << 24));
+        if (rc.bottom_smem) publish_smem(&sm.progress[w], 2 * mbx + 1, lane);
+        uint32_t r0 = pk4(v[4], v[5], v[6], v[7]), r1 = pk4(v[8], v[9], v[10], v[11]);
 
         uint2 top = make_uint2(0, 0);
         if (rc.top_smem) {
-            wait_smem(&sm.progress[w - 1], min(mbx + 2, g.mb_w), lane);
+            wait_smem(&sm.progress[w - 1], min(2 * mbx + 3, 2 * g.mb_w), lane);
             if (i < 4) {
                 const uint4 t4 = sm.ring[w - 1][mbx % kDbfRing][half][i];  // i = plane*2 + (row -2 | -1)
                 top = make_uint2(t4.x, t4.y);
@@ -473,12 +536,11 @@ __device__ __forceinline__ void deblock_chroma_row(DbfSmem &sm, const RowCtx rc,
                 *reinterpret_cast<uint32_t *>(Tt + 4) = top.y;
             }
             __syncwarp();
-            int c[10];
+            int c[8];
 #pragma unroll
-            for (int k = 0; k < 10; k++) c[k] = T[k * kCS2 + l];  // column l of this plane, rows -2..7
-            const EdgeParams p0 = edge_params((qc + qct + 1) >> 1, fd.alpha_off, fd.beta_off);
-            chroma_edge(c[0], c[1], c[2], c[3], bh0, p0.alpha, p0.beta, p0.tc0);
-            chroma_edge(c[4], c[5], c[6], c[7], bh2, pin.alpha, pin.beta, pin.tc0);
+            for (int k = 0; k < 8; k++) c[k] = T[k * kCS2 + l];  // column l of this plane, rows -2..5
+            chroma_edge_p(c[0], c[1], c[2], c[3], bh0, prm.y);
+            chroma_edge_p(c[4], c[5], c[6], c[7], bh2, prm.z);
             T[1 * kCS2 + l] = (uint8_t)c[1];
             T[2 * kCS2 + l] = (uint8_t)c[2];
             T[5 * kCS2 + l] = (uint8_t)c[5];
@@ -499,7 +561,7 @@ __device__ __forceinline__ void deblock_chroma_row(DbfSmem &sm, const RowCtx rc,
             if (last) __stcg(reinterpret_cast<uint32_t *>(grow + 8 * mbx + 4), r1);
         }
         if (rc.bottom_smem) {
-            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], mbx - kDbfRing + 1, lane);
+            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], 2 * (mbx - kDbfRing) + 2, lane);
             if (l >= 6) {
                 uint4 &slot = sm.ring[w][mbx % kDbfRing][half][pl * 2 + (l - 6)];
                 slot.x = r0;
@@ -509,12 +571,10 @@ __device__ __forceinline__ void deblock_chroma_row(DbfSmem &sm, const RowCtx rc,
         left = r1;
         own = nxt;
         bsw = bsw_n;
-        qpw = qpw_n;
+        prm = prm_n;
         dirty_prev = (any_v | any_h) != 0;
         if (rc.bottom_glob) __threadfence();
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) sm.progress[w] = mbx + 1;
+        publish_smem(&sm.progress[w], 2 * mbx + 2, lane);
         if (rc.bottom_glob && act && i == 0) st_release(prog + row, mbx + 1);
     }
 }

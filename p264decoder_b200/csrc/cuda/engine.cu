@@ -63,6 +63,13 @@ struct p264b200_engine {
     float prof_ms[K_COUNT] = {0, 0, 0, 0, 0};
     uint64_t prof_n[K_COUNT] = {0, 0, 0, 0, 0};
     uint64_t launches = 0;
+    // lane groups: independent lanes are split over `n_groups` CUDA streams so that one group's
+    // latency-bound wavefront kernels overlap with another group's MC kernel on the same SMs
+    static constexpr int kMaxGroups = 8;
+    int n_groups = 1;
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {};
+    bool groups_dirty = false;  // group streams hold work the main stream has not joined yet
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
 
     uint8_t *plane(int lane, int slot, int c) const
@@ -80,7 +87,8 @@ struct ProfScope {
     int kind;
     size_t idx = 0;
     bool on;
-    ProfScope(p264b200_engine *e_, int k) : e(e_), kind(k), on(e_->profile)
+    cudaStream_t st;
+    ProfScope(p264b200_engine *e_, int k, cudaStream_t s = nullptr) : e(e_), kind(k), on(e_->profile), st(s ? s : e_->stream)
     {
         e->launches++;
         if (!on) return;
@@ -95,13 +103,26 @@ struct ProfScope {
         idx = e->prof_used;
         e->prof_kind[idx / 2] = kind;
         e->prof_used += 2;
-        cudaEventRecord(e->prof_ev[idx], e->stream);
+        cudaEventRecord(e->prof_ev[idx], st);
     }
     ~ProfScope()
     {
-        if (on) cudaEventRecord(e->prof_ev[idx + 1], e->stream);
+        if (on) cudaEventRecord(e->prof_ev[idx + 1], st);
     }
 };
+
+// make the main stream wait for everything the lane-group streams were given
+cudaError_t join_groups(p264b200_engine *e)
+{
+    if (!e->groups_dirty) return cudaSuccess;
+    for (int gi = 0; gi < e->n_groups; gi++) {
+        cudaError_t err = cudaEventRecord(e->ev_join[gi], e->gstream[gi]);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(e->stream, e->ev_join[gi], 0);
+        if (err != cudaSuccess) return err;
+    }
+    e->groups_dirty = false;
+    return cudaSuccess;
+}
 
 void prof_collect(p264b200_engine *e)
 {
@@ -163,6 +184,12 @@ void p264b200_engine_destroy(p264b200_engine *e)
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (int gi = 0; gi < p264b200_engine::kMaxGroups; gi++) {
+        if (e->ev_join[gi]) cudaEventDestroy(e->ev_join[gi]);
+        if (e->ev_mc[gi]) cudaEventDestroy(e->ev_mc[gi]);
+        if (e->gstream[gi]) cudaStreamDestroy(e->gstream[gi]);
+    }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -183,6 +210,11 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!e) return P264B200_ENOMEM;
     e->cfg = *cfg;
     if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
+    e->n_groups = 1;  // measured: overlapping groups does not pay while both kernels are ALU-issue bound
+    if (const char *gq = getenv("P264B200_GROUPS")) e->n_groups = atoi(gq);
+    if (e->n_groups < 1) e->n_groups = 1;
+    if (e->n_groups > p264b200_engine::kMaxGroups) e->n_groups = p264b200_engine::kMaxGroups;
+    if (e->n_groups > cfg->lanes) e->n_groups = cfg->lanes;
     Geometry &g = e->g;
     g.mb_w = cfg->mb_w;
     g.mb_h = cfg->mb_h;
@@ -199,7 +231,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     e->coef_cap = (e->coef_cap + 7) & ~(size_t)7;
     const size_t frames = (size_t)cfg->lanes * cfg->n_slots;
     const size_t slots = (size_t)cfg->stage_steps * cfg->lanes;
-    e->sync_bytes = (4 + (size_t)cfg->lanes * 3 * g.mb_h) * sizeof(int);
+    e->sync_bytes = (4 * p264b200_engine::kMaxGroups + (size_t)cfg->lanes * 3 * g.mb_h) * sizeof(int);
     int rc = P264B200_OK;
     auto fail = [&](const char *what, cudaError_t err) {
         set_err(what, err);
@@ -218,6 +250,12 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaMalloc(&e->d_dqp, (size_t)cfg->lanes * n_mb * sizeof(uint32_t))) != cudaSuccess) fail("cudaMalloc dqp", err);
     if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
+    if (!rc && (err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    for (int gi = 0; gi < e->n_groups && !rc && e->n_groups > 1; gi++) {
+        if ((err = cudaStreamCreateWithFlags(&e->gstream[gi], cudaStreamNonBlocking)) != cudaSuccess) fail("group stream", err);
+        if (!rc && (err = cudaEventCreateWithFlags(&e->ev_join[gi], cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+        if (!rc && (err = cudaEventCreateWithFlags(&e->ev_mc[gi], cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    }
     if (!rc) {
         // grey frames so that never-written slots are deterministic
         if ((err = cudaMemsetAsync(e->d_y, 128, frames * g.y_plane, e->stream)) != cudaSuccess) fail("memset", err);
@@ -259,6 +297,7 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     for (int i = 0; i < h.num_ref; i++)
         if (h.ref_slot[i] < 0 || h.ref_slot[i] >= e->cfg.n_slots) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
+    CK(join_groups(e));
     const size_t n_mb = (size_t)g.mb_w * g.mb_h;
     const size_t s = (size_t)step * e->cfg.lanes + lane;
     p264b200_mb *d_mbs = e->d_mbs + s * n_mb;
@@ -273,7 +312,7 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     for (int c = 0; c < 3; c++) d.cur[c] = e->plane(lane, h.dst_slot, c);
     for (int i = 0; i < h.num_ref; i++)
         for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
-    d.row_progress = e->d_sync + 4 + (size_t)lane * 3 * g.mb_h;
+    d.row_progress = e->d_sync + 4 * p264b200_engine::kMaxGroups + (size_t)lane * 3 * g.mb_h;
     d.dbf_bs = e->d_bs + (size_t)lane * n_mb;
     d.dbf_qp = e->d_dqp + (size_t)lane * n_mb;
     d.slice_type = h.slice_type;
@@ -294,34 +333,62 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
     CK(cudaSetDevice(e->cfg.device));
     const Geometry &g = e->g;
     const int n_mb = g.mb_w * g.mb_h;
-    const FrameDesc *descs = e->d_descs + (size_t)step * e->cfg.lanes;
-    unsigned flags = 0;
-    for (int l = 0; l < n_lanes; l++) flags |= e->slot_flags[(size_t)step * e->cfg.lanes + l];
-    const bool intra = flags & 1, dbf = flags & 2, pslice = flags & 4;
-    if (intra || dbf) CK(cudaMemsetAsync(e->d_sync, 0, e->sync_bytes, e->stream));
-    if (pslice) {
-        ProfScope p(e, K_INTER);
-        dim3 grid((n_mb + kMbPerCta - 1) / kMbPerCta, n_lanes);
-        recon_inter_kernel<<<grid, kInterThreads, 0, e->stream>>>(descs, g);
+    const FrameDesc *descs0 = e->d_descs + (size_t)step * e->cfg.lanes;
+    const int G = n_lanes >= 2 * e->n_groups ? e->n_groups : 1;
+    // the group streams run ahead of each other across steps (no per-step barrier): a group only
+    // waits for the staging copies issued on the main stream so far and for its own previous work
+    if (G > 1) CK(cudaEventRecord(e->ev_fork, e->stream));
+    else {
+        CK(join_groups(e));
+        CK(cudaMemsetAsync(e->d_sync, 0, e->sync_bytes, e->stream));
     }
-    if (intra) {
-        ProfScope p(e, K_INTRA);
-        recon_intra_kernel<<<g.mb_h * n_lanes, 32, 0, e->stream>>>(descs, g, e->d_sync + 0);
-    }
-    if (dbf) {
-        {
-            ProfScope p(e, K_DEBLOCK_BS);
-            deblock_bs_kernel<<<dim3((4 * n_mb + 255) / 256, n_lanes), 256, 0, e->stream>>>(descs, g);
+    const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
+                      2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
+    for (int gi = 0; gi < G; gi++) {
+        // lanes [l0, l1) of this group; pairs of lanes share a deblock warp, so groups start on even lanes
+        const int per = ((n_lanes + G - 1) / G + 1) & ~1;
+        const int l0 = gi * per, l1 = l0 + per < n_lanes ? l0 + per : n_lanes;
+        if (l0 >= l1) break;
+        const int nl = l1 - l0;
+        cudaStream_t st = G > 1 ? e->gstream[gi] : e->stream;
+        if (G > 1) {
+            CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+            // wavefront state of this group's lanes + its tickets
+            CK(cudaMemsetAsync(e->d_sync + 4 * gi, 0, 4 * sizeof(int), st));
+            CK(cudaMemsetAsync(e->d_sync + 4 * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), st));
+            // stagger: this group's MC starts when the previous group's MC is done, so that MC (issue-bound)
+            // of one group overlaps the latency-bound wavefronts of the others instead of all groups moving in phase
+            if (gi > 0) CK(cudaStreamWaitEvent(st, e->ev_mc[gi - 1], 0));
         }
-        ProfScope p(e, K_DEBLOCK);
-        deblock_kernel<<<2 * ((n_lanes + 1) / 2) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfRows, 0, e->stream>>>(descs, g, n_lanes, e->d_sync + 1, e->dbg);
-    }
-    {
-        ProfScope p(e, K_BORDER);
-        const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
-                          2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
-        dim3 grid((words + 255) / 256, n_lanes);
-        border_kernel<<<grid, 256, 0, e->stream>>>(descs, g, nullptr, nullptr, nullptr);
+        unsigned flags = 0;
+        for (int l = l0; l < l1; l++) flags |= e->slot_flags[(size_t)step * e->cfg.lanes + l];
+        const bool intra = flags & 1, dbf = flags & 2, pslice = flags & 4;
+        const FrameDesc *descs = descs0 + l0;
+        int *tickets = e->d_sync + 4 * gi;
+        if (pslice) {
+            ProfScope p(e, K_INTER, st);
+            dim3 grid((n_mb + kMbPerCta - 1) / kMbPerCta, nl);
+            recon_inter_kernel<<<grid, kInterThreads, 0, st>>>(descs, g);
+        }
+        if (G > 1) CK(cudaEventRecord(e->ev_mc[gi], st));
+        if (dbf) {
+            ProfScope p(e, K_DEBLOCK_BS, st);
+            deblock_bs_kernel<<<dim3((4 * n_mb + 255) / 256, nl), 256, 0, st>>>(descs, g);
+        }
+        if (intra) {
+            ProfScope p(e, K_INTRA, st);
+            recon_intra_kernel<<<g.mb_h * nl, 32, 0, st>>>(descs, g, tickets + 0);
+        }
+        if (dbf) {
+            ProfScope p(e, K_DEBLOCK, st);
+            deblock_kernel<<<2 * ((nl + 1) / 2) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfRows, 0, st>>>(descs, g, nl, tickets + 1, e->dbg);
+        }
+        {
+            ProfScope p(e, K_BORDER, st);
+            dim3 grid((words + 255) / 256, nl);
+            border_kernel<<<grid, 256, 0, st>>>(descs, g, nullptr, nullptr, nullptr);
+        }
+        if (G > 1) e->groups_dirty = true;
     }
     CK(cudaGetLastError());
     return P264B200_OK;
@@ -342,6 +409,7 @@ int p264b200_frame_upload(p264b200_engine *e, int lane, int slot, const uint8_t 
 {
     if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
+    CK(join_groups(e));
     const Geometry &g = e->g;
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 0), g.y_stride, y, y_stride, g.width, g.height, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 1), g.c_stride, u, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
@@ -360,6 +428,7 @@ int p264b200_frame_download(p264b200_engine *e, int lane, int slot, uint8_t *y, 
 {
     if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
+    CK(join_groups(e));
     const Geometry &g = e->g;
     CK(cudaMemcpy2DAsync(y, y_stride, e->plane(lane, slot, 0), g.y_stride, g.width, g.height, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpy2DAsync(u, c_stride, e->plane(lane, slot, 1), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->stream));
@@ -371,6 +440,7 @@ int p264b200_engine_sync(p264b200_engine *e)
 {
     if (!e) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
+    CK(join_groups(e));
     CK(cudaStreamSynchronize(e->stream));
     if (e->profile) prof_collect(e);
     return P264B200_OK;
@@ -381,12 +451,14 @@ void *p264b200_engine_stream(p264b200_engine *e) { return e ? (void *)e->stream 
 int p264b200_timer_start(p264b200_engine *e)
 {
     if (!e) return P264B200_EINVAL;
+    CK(join_groups(e));
     CK(cudaEventRecord(e->ev0, e->stream));
     return P264B200_OK;
 }
 int p264b200_timer_stop(p264b200_engine *e, float *ms)
 {
     if (!e || !ms) return P264B200_EINVAL;
+    CK(join_groups(e));
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaEventSynchronize(e->ev1));
     CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));

@@ -227,7 +227,7 @@ __device__ __forceinline__ void mc_chroma_2x2(const uint8_t *__restrict__ src, i
 }
 
 #ifdef P264B200_DEFINE_KERNELS
-__global__ void __launch_bounds__(kInterThreads) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g)
+__global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g)
 {
     constexpr int kKeys = 11;           // (coded ? 0 : 5) + class, 10 = nothing to do
     __shared__ int s_cnt[4][12];        // [luma warp][key], then exclusive start of (key, warp)

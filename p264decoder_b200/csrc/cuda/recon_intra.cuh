@@ -328,8 +328,13 @@ __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__rest
             mask &= mask - 1;
             if (row > 0) {
                 const int need = min(mbx + 2, g.mb_w);
-                if (lane == 0)
-                    while (ld_acquire(prog + row - 1) < need) __nanosleep(64);
+                if (lane == 0) {
+                    unsigned ns = 64;
+                    while (ld_acquire(prog + row - 1) < need) {
+                        __nanosleep(ns);
+                        if (ns < 4096) ns <<= 1;
+                    }
+                }
                 __syncwarp();
             }
             recon_intra_mb(s, fd, g, mbs[mbx], mbx, row, lane);
