@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--staged", type=int, default=4, help="distinct pre-staged pictures per lane (cycled)")
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-parts", default="hcd", help="debug: which legs the e2e step runs (h = H2D, c = compute, d = D2H)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="pictures per core in the CPU baseline (0 = auto)")
     return ap.parse_args()
@@ -272,7 +273,8 @@ def run_b200(args, rank, world, local_rank):
             fss[t][l] = fs
     del coef_tmp
     coef_slots_per_step = total_coef / T            # int16 slots per step over all lanes
-    h2d_per_step = L * n_mb * 96 + 2 * coef_slots_per_step + L * 512
+    # the batched stage call copies the records, the coefficient area up to the last lane's end and the descriptors
+    h2d_per_step = L * n_mb * 96 + 2 * ((L - 1) * coef_cap + coef_slots_per_step / L) + L * 440
 
     eng = P.Engine(mb_w, mb_h, n_slots=n_slots, lanes=L, stage_steps=T, coef_capacity=coef_cap, device=local_rank)
     pics = [P.smooth_picture(16 * mb_w, 16 * mb_h, seed=rank * 1000 + i) for i in range(4)]
@@ -317,14 +319,23 @@ def run_b200(args, rank, world, local_rank):
         fsz = W * H * 3 // 2
         base = out_host.ctypes.data
 
+        fs_arrays, slot_arrays = [], []
+        for t in range(T):
+            arr = (P.FrameSyntax * L)(*fss[t])
+            fs_arrays.append(arr)
+            slot_arrays.append((C.c_int32 * L)(*[fss[t][l].hdr.dst_slot for l in range(L)]))
+
         def e2e_step(i):
             t = i % T
-            for l in range(L):
-                eng.stage(t, l, fss[t][l])                      # H2D of this step's inputs (pinned)
-            eng.recon_step(t, L)
-            for l in range(L):
-                p = base + l * fsz
-                lib.p264b200_frame_download(eng._e, l, fss[t][l].hdr.dst_slot, p + yo, W, p + uo, p + vo, W // 2)
+            rc = 0
+            if "h" in args.e2e_parts:
+                rc |= lib.p264b200_stage_frames(eng._e, t, L, fs_arrays[t])        # H2D of this step's inputs (pinned)
+            if "c" in args.e2e_parts:
+                rc |= lib.p264b200_recon_step(eng._e, t, L)
+            if "d" in args.e2e_parts:
+                rc |= lib.p264b200_frames_download(eng._e, L, slot_arrays[t], base, fsz)  # D2H of every picture
+            if rc:
+                raise RuntimeError(lib.p264b200_last_error().decode())
 
         for i in range(max(1, min(args.warmup, 3))):
             e2e_step(i)
@@ -336,7 +347,7 @@ def run_b200(args, rank, world, local_rank):
         e2e_total = eng.timer_stop()
         barrier()
         e2e_ms = e2e_total / n_e2e
-        assert int(out_host[:W].astype(np.int64).sum()) > 0
+        assert "d" not in args.e2e_parts or int(out_host[:W].astype(np.int64).sum()) > 0
 
     # ---- max over ranks
     ms_step = ms / args.steps

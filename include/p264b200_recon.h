@@ -141,9 +141,16 @@ void p264b200_engine_destroy(p264b200_engine *e);
 int  p264b200_engine_geometry(const p264b200_engine *e, int32_t *luma_stride, int32_t *chroma_stride,
                               int32_t *width, int32_t *height);
 
-/* Copy one picture's syntax from HOST memory into staging step `step` of lane `lane`
- * (asynchronous on the engine stream when the source is pinned). */
+/* Copy one picture's syntax from HOST memory into staging step `step` of lane `lane`.
+ * Asynchronous when the source is pinned.  Uploads, kernels and downloads run on three internal
+ * streams ordered by events, so H2D of step n+1, reconstruction of step n and D2H of step n-1
+ * overlap; a staging step may be re-staged as soon as the call returns (the copy waits on the device
+ * for the reconstruction that last used it), but the HOST buffers must stay untouched until
+ * p264b200_engine_sync. */
 int  p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs);
+
+/* Batched form: lanes [0, n) of one step from an array of n FrameSyntax (one call instead of n). */
+int  p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_frame_syntax *fs);
 
 /* Reconstruct staging step `step` for lanes [0, n_lanes): MC + IDCT + intra + deblock + border.
  * Asynchronous; inputs are already resident in HBM. */
@@ -158,6 +165,10 @@ int  p264b200_frame_upload(p264b200_engine *e, int lane, int slot,
                            const uint8_t *y, int y_stride, const uint8_t *u, const uint8_t *v, int c_stride);
 int  p264b200_frame_download(p264b200_engine *e, int lane, int slot,
                              uint8_t *y, int y_stride, uint8_t *u, uint8_t *v, int c_stride);
+
+/* Batched download: picture of lane l (ring slot slots[l]) into dst + l * picture_bytes as a tight
+ * I420 image (Y, then U, then V); picture_bytes >= width*height*3/2. */
+int  p264b200_frames_download(p264b200_engine *e, int n, const int32_t *slots, uint8_t *dst, size_t picture_bytes);
 
 int  p264b200_engine_sync(p264b200_engine *e);
 

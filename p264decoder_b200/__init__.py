@@ -131,6 +131,8 @@ def load_library() -> C.CDLL:
         "p264b200_engine_geometry": (i32, [vp] + [C.POINTER(C.c_int32)] * 4),
         "p264b200_stage_frame": (i32, [vp, i32, i32, C.POINTER(FrameSyntax)]),
         "p264b200_recon_step": (i32, [vp, i32, i32]),
+        "p264b200_stage_frames": (i32, [vp, i32, i32, C.POINTER(FrameSyntax)]),
+        "p264b200_frames_download": (i32, [vp, i32, C.POINTER(C.c_int32), u8p, C.c_size_t]),
         "p264b200_recon_frame": (i32, [vp, i32, C.POINTER(FrameSyntax)]),
         "p264b200_frame_upload": (i32, [vp, i32, i32, u8p, i32, u8p, u8p, i32]),
         "p264b200_frame_download": (i32, [vp, i32, i32, u8p, i32, u8p, u8p, i32]),

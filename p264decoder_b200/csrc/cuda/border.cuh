@@ -56,6 +56,35 @@ __global__ void __launch_bounds__(256) border_kernel(const FrameDesc *__restrict
         border_plane_word(pl[2], g.c_stride, g.width / 2, g.height / 2, kChromaPad, idx - ny - nc);
 }
 
+// Output packing for the batched download: padded planes of `n` pictures -> tight I420 images in one
+// contiguous device buffer (Y, U, V back to back), so that the host copy is a single large DMA instead
+// of three pitched 2-D copies per picture.  128-bit loads and stores (16 samples per thread).
+struct PackSrc {
+    const uint8_t *plane[3];
+};
+constexpr int kPackMaxLanes = 256;
+struct PackSel {
+    uint8_t slot[kPackMaxLanes];  // ring slot to read for every lane (kernel argument, no staging copy)
+};
+// table: [lane * n_slots + slot] plane origins, filled once at engine creation
+__global__ void __launch_bounds__(256) pack_i420_kernel(const PackSrc *__restrict__ table, int n_slots, PackSel sel, Geometry g,
+                                                        uint8_t *__restrict__ dst, size_t picture_bytes)
+{
+    const PackSrc s = table[blockIdx.y * n_slots + sel.slot[blockIdx.y]];
+    uint8_t *out = dst + (size_t)blockIdx.y * picture_bytes;
+    const int yv = (g.width >> 4) * g.height;                 // uint4 per luma plane
+    const int cv = (g.width >> 5) * (g.height >> 1);          // uint4 per chroma plane
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < yv + 2 * cv; i += gridDim.x * blockDim.x) {
+        if (i < yv) {
+            const int wv = g.width >> 4, r = i / wv, c = i % wv;
+            reinterpret_cast<uint4 *>(out)[i] = *reinterpret_cast<const uint4 *>(s.plane[0] + (size_t)r * g.y_stride + 16 * c);
+        } else {
+            const int j = i - yv, p = j >= cv, k = j - p * cv, wv = g.width >> 5, r = k / wv, c = k % wv;
+            reinterpret_cast<uint4 *>(out + (size_t)g.width * g.height + (size_t)p * (g.width / 2) * (g.height / 2))[k] =
+                *reinterpret_cast<const uint4 *>(s.plane[1 + p] + (size_t)r * g.c_stride + 16 * c);
+        }
+    }
+}
 #endif  // P264B200_DEFINE_KERNELS
 
 }  // namespace p264b200

@@ -41,7 +41,17 @@ enum { K_INTER = 0, K_INTRA, K_DEBLOCK, K_BORDER, K_DEBLOCK_BS, K_COUNT };
 struct p264b200_engine {
     p264b200_engine_cfg cfg;
     Geometry g;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                 // compute (kernels)
+    // Host-buffer path: syntax uploads, kernels and picture downloads run on three streams so that
+    // H2D of step n+1, reconstruction of step n and D2H of step n-1 overlap (PCIe is full duplex).
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_staged;            // [step] last upload into that staging slot
+    std::vector<cudaEvent_t> ev_recon;             // [step] reconstruction that consumed that slot
+    std::vector<cudaEvent_t> ev_d2h_slot;          // [frame slot] last download of that ring slot (any lane)
+    cudaEvent_t ev_compute = nullptr;              // last reconstruction issued
+    std::vector<uint32_t> step_dst_mask;           // [step] ring slots written by that step
+    std::vector<uint8_t> staged_dirty, d2h_dirty;  // event recorded since creation?
+    bool h2d_busy = false, d2h_busy = false;
     // frame store
     uint8_t *d_y = nullptr, *d_c = nullptr;
     // staging: [step][lane]
@@ -49,6 +59,9 @@ struct p264b200_engine {
     int16_t *d_coefs = nullptr;
     FrameDesc *d_descs = nullptr, *h_descs = nullptr;
     size_t coef_cap = 0;  // int16 per lane per step
+    uint8_t *d_out = nullptr;      // [lanes] tight I420 pictures for the batched download (lazy)
+    size_t out_bytes = 0;
+    PackSrc *d_pack = nullptr;     // [lanes][n_slots] plane origins
     DeblockSide *d_bs = nullptr;   // [lanes][n_mb]
     uint32_t *d_dqp = nullptr;     // [lanes][n_mb]
     int *d_sync = nullptr;  // [4 tickets/pad][lanes][3*mb_h]: intra, luma deblock, chroma deblock wavefronts
@@ -179,9 +192,19 @@ void p264b200_engine_destroy(p264b200_engine *e)
     cudaFree(e->d_descs);
     cudaFree(e->d_sync);
     cudaFree(e->d_bs);
+    cudaFree(e->d_out);
+    cudaFree(e->d_pack);
     cudaFree(e->d_dqp);
     if (e->h_descs) cudaFreeHost(e->h_descs);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    if (e->s_h2d) cudaStreamSynchronize(e->s_h2d);
+    if (e->s_d2h) cudaStreamSynchronize(e->s_d2h);
+    for (auto *vec : {&e->ev_staged, &e->ev_recon, &e->ev_d2h_slot})
+        for (auto ev : *vec)
+            if (ev) cudaEventDestroy(ev);
+    if (e->ev_compute) cudaEventDestroy(e->ev_compute);
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -248,6 +271,18 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaMalloc(&e->d_sync, e->sync_bytes)) != cudaSuccess) fail("cudaMalloc sync", err);
     if (!rc && (err = cudaMalloc(&e->d_bs, (size_t)cfg->lanes * n_mb * sizeof(DeblockSide))) != cudaSuccess) fail("cudaMalloc bs", err);
     if (!rc && (err = cudaMalloc(&e->d_dqp, (size_t)cfg->lanes * n_mb * sizeof(uint32_t))) != cudaSuccess) fail("cudaMalloc dqp", err);
+    if (!rc && (err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
+    if (!rc && (err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
+    if (!rc && (err = cudaEventCreateWithFlags(&e->ev_compute, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    e->ev_staged.assign(cfg->stage_steps, nullptr);
+    e->ev_recon.assign(cfg->stage_steps, nullptr);
+    e->ev_d2h_slot.assign(cfg->n_slots, nullptr);
+    for (auto *vec : {&e->ev_staged, &e->ev_recon, &e->ev_d2h_slot})
+        for (auto &ev : *vec)
+            if (!rc && (err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    e->step_dst_mask.assign(cfg->stage_steps, 0);
+    e->staged_dirty.assign(cfg->stage_steps, 0);
+    e->d2h_dirty.assign(cfg->n_slots, 0);
     if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
@@ -283,9 +318,12 @@ int p264b200_engine_geometry(const p264b200_engine *e, int32_t *luma_stride, int
     return P264B200_OK;
 }
 
-int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs)
+}  // extern "C" (reopened below)
+
+namespace {
+// validation + FrameDesc of one lane's picture (no copies)
+int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs)
 {
-    if (!e || !fs || step < 0 || step >= e->cfg.stage_steps || lane < 0 || lane >= e->cfg.lanes) return P264B200_EINVAL;
     const p264b200_frame_hdr &h = fs->hdr;
     const Geometry &g = e->g;
     if (h.mb_w != g.mb_w || h.mb_h != g.mb_h || h.dst_slot < 0 || h.dst_slot >= e->cfg.n_slots || h.num_ref < 0 ||
@@ -296,19 +334,12 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     if (h.slice_type == P264B200_SLICE_P && h.num_ref < 1) return P264B200_EINVAL;
     for (int i = 0; i < h.num_ref; i++)
         if (h.ref_slot[i] < 0 || h.ref_slot[i] >= e->cfg.n_slots) return P264B200_EINVAL;
-    CK(cudaSetDevice(e->cfg.device));
-    CK(join_groups(e));
     const size_t n_mb = (size_t)g.mb_w * g.mb_h;
     const size_t s = (size_t)step * e->cfg.lanes + lane;
-    p264b200_mb *d_mbs = e->d_mbs + s * n_mb;
-    int16_t *d_coefs = e->d_coefs + s * e->coef_cap;
-    CK(cudaMemcpyAsync(d_mbs, fs->mbs, n_mb * sizeof(p264b200_mb), cudaMemcpyHostToDevice, e->stream));
-    if (h.n_coef)
-        CK(cudaMemcpyAsync(d_coefs, fs->coefs, (size_t)h.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
     FrameDesc &d = e->h_descs[s];
     memset(&d, 0, sizeof(d));
-    d.mbs = d_mbs;
-    d.coefs = d_coefs;
+    d.mbs = e->d_mbs + s * n_mb;
+    d.coefs = e->d_coefs + s * e->coef_cap;
     for (int c = 0; c < 3; c++) d.cur[c] = e->plane(lane, h.dst_slot, c);
     for (int i = 0; i < h.num_ref; i++)
         for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
@@ -322,8 +353,65 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     d.chroma_qp_off = h.chroma_qp_index_offset;
     d.n_intra = h.n_intra;
     d.num_ref = h.num_ref;
-    CK(cudaMemcpyAsync(e->d_descs + s, &d, sizeof(FrameDesc), cudaMemcpyHostToDevice, e->stream));
     e->slot_flags[s] = (uint8_t)((h.n_intra > 0) | ((h.deblock != 0) << 1) | ((h.slice_type == P264B200_SLICE_P) << 2));
+    if (lane == 0) e->step_dst_mask[step] = 0;
+    e->step_dst_mask[step] |= 1u << h.dst_slot;
+    return P264B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs)
+{
+    if (!e || !fs || step < 0 || step >= e->cfg.stage_steps || lane < 0 || lane >= e->cfg.lanes) return P264B200_EINVAL;
+    const int r = prepare_desc(e, step, lane, fs);
+    if (r) return r;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t n_mb = (size_t)e->g.mb_w * e->g.mb_h;
+    const size_t s = (size_t)step * e->cfg.lanes + lane;
+    // the staging slot may still be read by the reconstruction that last used it
+    CK(cudaStreamWaitEvent(e->s_h2d, e->ev_recon[step], 0));
+    CK(cudaMemcpyAsync(e->d_mbs + s * n_mb, fs->mbs, n_mb * sizeof(p264b200_mb), cudaMemcpyHostToDevice, e->s_h2d));
+    if (fs->hdr.n_coef)
+        CK(cudaMemcpyAsync(e->d_coefs + s * e->coef_cap, fs->coefs, (size_t)fs->hdr.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaMemcpyAsync(e->d_descs + s, &e->h_descs[s], sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
+    e->h2d_busy = true;
+    return P264B200_OK;
+}
+
+int p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_frame_syntax *fs)
+{
+    if (!e || !fs || n < 1 || n > e->cfg.lanes || step < 0 || step >= e->cfg.stage_steps) return P264B200_EINVAL;
+    const size_t n_mb = (size_t)e->g.mb_w * e->g.mb_h;
+    // host buffers laid out like the device staging area ([lane][n_mb] records, [lane][coef_capacity] levels):
+    // three copies for the whole step instead of three per lane (the per-call cost of ~200 small copies,
+    // not PCIe, was the limit of the host-buffer path)
+    bool contiguous = true;
+    for (int l = 1; l < n && contiguous; l++)
+        contiguous = fs[l].mbs == fs[0].mbs + (size_t)l * n_mb && fs[l].coefs == fs[0].coefs + (size_t)l * e->coef_cap;
+    if (!contiguous) {
+        for (int l = 0; l < n; l++) {
+            const int r = p264b200_stage_frame(e, step, l, fs + l);
+            if (r) return r;
+        }
+        return P264B200_OK;
+    }
+    for (int l = 0; l < n; l++) {
+        const int r = prepare_desc(e, step, l, fs + l);
+        if (r) return r;
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t s0 = (size_t)step * e->cfg.lanes;
+    CK(cudaStreamWaitEvent(e->s_h2d, e->ev_recon[step], 0));
+    CK(cudaMemcpyAsync(e->d_mbs + s0 * n_mb, fs[0].mbs, (size_t)n * n_mb * sizeof(p264b200_mb), cudaMemcpyHostToDevice, e->s_h2d));
+    const size_t coef_span = (size_t)(n - 1) * e->coef_cap + fs[n - 1].hdr.n_coef;
+    if (coef_span)
+        CK(cudaMemcpyAsync(e->d_coefs + s0 * e->coef_cap, fs[0].coefs, coef_span * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
+    e->h2d_busy = true;
     return P264B200_OK;
 }
 
@@ -333,6 +421,9 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
     CK(cudaSetDevice(e->cfg.device));
     const Geometry &g = e->g;
     const int n_mb = g.mb_w * g.mb_h;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_staged[step], 0));
+    for (int sl = 0; sl < e->cfg.n_slots; sl++)
+        if (e->step_dst_mask[step] >> sl & 1) CK(cudaStreamWaitEvent(e->stream, e->ev_d2h_slot[sl], 0));
     const FrameDesc *descs0 = e->d_descs + (size_t)step * e->cfg.lanes;
     const int G = n_lanes >= 2 * e->n_groups ? e->n_groups : 1;
     // the group streams run ahead of each other across steps (no per-step barrier): a group only
@@ -390,6 +481,9 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (G > 1) e->groups_dirty = true;
     }
+    if (G > 1) CK(join_groups(e));
+    CK(cudaEventRecord(e->ev_recon[step], e->stream));
+    CK(cudaEventRecord(e->ev_compute, e->stream));
     CK(cudaGetLastError());
     return P264B200_OK;
 }
@@ -410,6 +504,7 @@ int p264b200_frame_upload(p264b200_engine *e, int lane, int slot, const uint8_t 
     if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
     CK(join_groups(e));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_d2h_slot[slot], 0));
     const Geometry &g = e->g;
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 0), g.y_stride, y, y_stride, g.width, g.height, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 1), g.c_stride, u, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
@@ -428,11 +523,61 @@ int p264b200_frame_download(p264b200_engine *e, int lane, int slot, uint8_t *y, 
 {
     if (!e || !y || !u || !v || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
-    CK(join_groups(e));
     const Geometry &g = e->g;
-    CK(cudaMemcpy2DAsync(y, y_stride, e->plane(lane, slot, 0), g.y_stride, g.width, g.height, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpy2DAsync(u, c_stride, e->plane(lane, slot, 1), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpy2DAsync(v, c_stride, e->plane(lane, slot, 2), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamWaitEvent(e->s_d2h, e->ev_compute, 0));
+    CK(cudaMemcpy2DAsync(y, y_stride, e->plane(lane, slot, 0), g.y_stride, g.width, g.height, cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaMemcpy2DAsync(u, c_stride, e->plane(lane, slot, 1), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaMemcpy2DAsync(v, c_stride, e->plane(lane, slot, 2), g.c_stride, g.width / 2, g.height / 2, cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaEventRecord(e->ev_d2h_slot[slot], e->s_d2h));
+    e->d2h_busy = true;
+    return P264B200_OK;
+}
+
+int p264b200_frames_download(p264b200_engine *e, int n, const int32_t *slots, uint8_t *dst, size_t picture_bytes)
+{
+    if (!e || !slots || !dst || n < 1 || n > e->cfg.lanes) return P264B200_EINVAL;
+    const Geometry &g = e->g;
+    const size_t ysz = (size_t)g.width * g.height;
+    if (picture_bytes < ysz * 3 / 2 || (picture_bytes & 15) || (g.width & 31) || n > kPackMaxLanes) {
+        // odd geometry: fall back to per-picture pitched copies
+        if (picture_bytes < ysz * 3 / 2) return P264B200_EINVAL;
+        for (int l = 0; l < n; l++) {
+            uint8_t *p = dst + (size_t)l * picture_bytes;
+            const int r = p264b200_frame_download(e, l, slots[l], p, g.width, p + ysz, p + ysz + ysz / 4, g.width / 2);
+            if (r) return r;
+        }
+        return P264B200_OK;
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t need = (size_t)e->cfg.lanes * picture_bytes;
+    if (need > e->out_bytes) {
+        CK(cudaStreamSynchronize(e->s_d2h));
+        cudaFree(e->d_out);
+        e->d_out = nullptr;
+        CK(cudaMalloc(&e->d_out, need));
+        e->out_bytes = need;
+    }
+    if (!e->d_pack) {
+        std::vector<PackSrc> tab((size_t)e->cfg.lanes * e->cfg.n_slots);
+        for (int l = 0; l < e->cfg.lanes; l++)
+            for (int sl = 0; sl < e->cfg.n_slots; sl++)
+                for (int c = 0; c < 3; c++) tab[(size_t)l * e->cfg.n_slots + sl].plane[c] = e->plane(l, sl, c);
+        CK(cudaMalloc(&e->d_pack, tab.size() * sizeof(PackSrc)));
+        CK(cudaMemcpy(e->d_pack, tab.data(), tab.size() * sizeof(PackSrc), cudaMemcpyHostToDevice));
+    }
+    PackSel sel;
+    for (int l = 0; l < n; l++) {
+        if (slots[l] < 0 || slots[l] >= e->cfg.n_slots) return P264B200_EINVAL;
+        sel.slot[l] = (uint8_t)slots[l];
+    }
+    CK(cudaStreamWaitEvent(e->s_d2h, e->ev_compute, 0));
+    e->launches++;
+    pack_i420_kernel<<<dim3(64, n), 256, 0, e->s_d2h>>>(e->d_pack, e->cfg.n_slots, sel, g, e->d_out, picture_bytes);
+    CK(cudaGetLastError());
+    // the ring slots are free again as soon as the pack kernel has read them
+    for (int l = 0; l < n; l++) CK(cudaEventRecord(e->ev_d2h_slot[slots[l]], e->s_d2h));
+    CK(cudaMemcpyAsync(dst, e->d_out, (size_t)n * picture_bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+    e->d2h_busy = true;
     return P264B200_OK;
 }
 
@@ -441,7 +586,10 @@ int p264b200_engine_sync(p264b200_engine *e)
     if (!e) return P264B200_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
     CK(join_groups(e));
+    CK(cudaStreamSynchronize(e->s_h2d));
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->s_d2h));
+    e->h2d_busy = e->d2h_busy = false;
     if (e->profile) prof_collect(e);
     return P264B200_OK;
 }
@@ -452,13 +600,27 @@ int p264b200_timer_start(p264b200_engine *e)
 {
     if (!e) return P264B200_EINVAL;
     CK(join_groups(e));
+    CK(cudaStreamSynchronize(e->s_h2d));
+    CK(cudaStreamSynchronize(e->s_d2h));
+    CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
+    // uploads / downloads issued from now on are ordered after the start mark
+    CK(cudaStreamWaitEvent(e->s_h2d, e->ev0, 0));
+    CK(cudaStreamWaitEvent(e->s_d2h, e->ev0, 0));
     return P264B200_OK;
 }
 int p264b200_timer_stop(p264b200_engine *e, float *ms)
 {
     if (!e || !ms) return P264B200_EINVAL;
     CK(join_groups(e));
+    {
+        // the stop mark waits for the copy streams too, so the interval covers H2D + kernels + D2H
+        cudaEvent_t a = e->ev_staged[0], b = e->ev_d2h_slot[0];
+        CK(cudaEventRecord(a, e->s_h2d));
+        CK(cudaEventRecord(b, e->s_d2h));
+        CK(cudaStreamWaitEvent(e->stream, a, 0));
+        CK(cudaStreamWaitEvent(e->stream, b, 0));
+    }
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaEventSynchronize(e->ev1));
     CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));

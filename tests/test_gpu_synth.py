@@ -76,3 +76,33 @@ def test_1080p_stream():
 
 def test_4k_multiref_two_pictures():
     _run_stream(240, 135, 2, n_refs=4, seed=2160, sweep_offsets=1, first_intra=0)
+
+
+def test_batched_stage_and_packed_download_match_per_picture_path():
+    """p264b200_stage_frames / p264b200_frames_download (pack kernel + one contiguous D2H) against the
+    per-picture calls, pipelined over several steps without intermediate syncs."""
+    import ctypes as C
+
+    mb_w, mb_h, lanes, steps = 10, 6, 6, 4
+    lib = P.load_library()
+    eng = P.Engine(mb_w, mb_h, n_slots=2, lanes=lanes, stage_steps=2)
+    rings = [O.OracleFrames(mb_w, mb_h, 2) for _ in range(lanes)]
+    syns = [P.Synth(mb_w, mb_h, n_refs=1, seed=77 + l, intra_pct=5) for l in range(lanes)]
+    W, H = 16 * mb_w, 16 * mb_h
+    fsz = W * H * 3 // 2
+    outs = [np.zeros(lanes * fsz, np.uint8) for _ in range(steps)]
+    keep, want = [], []
+    for s in range(steps):
+        frames = [sy.next() for sy in syns]
+        keep.append(frames)  # host buffers must stay alive until the sync
+        arr = (P.FrameSyntax * lanes)(*[f.syntax() for f in frames])
+        slots = (C.c_int32 * lanes)(*[f.hdr.dst_slot for f in frames])
+        assert lib.p264b200_stage_frames(eng._e, s % 2, lanes, arr) == 0
+        assert lib.p264b200_recon_step(eng._e, s % 2, lanes) == 0
+        assert lib.p264b200_frames_download(eng._e, lanes, slots, outs[s].ctypes.data, fsz) == 0
+        want.append([np.concatenate([p.ravel() for p in rings[l].recon(frames[l])]) for l in range(lanes)])
+    eng.sync()
+    for s in range(steps):
+        for l in range(lanes):
+            assert np.array_equal(outs[s][l * fsz : (l + 1) * fsz], want[s][l]), f"step {s} lane {l}"
+    eng.close()
