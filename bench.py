@@ -173,7 +173,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": f"reconstructed_{args.size}_frames_per_s", "value": fps, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * float(np.mean([v[1] for v in vals])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, lanes=cores),
+        "config": workload_config(args, lanes=args.lanes),
         "cpu_baseline": {"value": fps, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
