@@ -458,8 +458,8 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         int *tickets = e->d_sync + 4 * gi;
         if (pslice) {
             ProfScope p(e, K_INTER, st);
-            dim3 grid((n_mb + kMbPerCta - 1) / kMbPerCta, nl);
-            recon_inter_kernel<<<grid, kInterThreads, 0, st>>>(descs, g);
+            const int tiles_x = (g.mb_w + kTileW - 1) / kTileW, tiles_y = (g.mb_h + kTileH - 1) / kTileH;
+            recon_inter_kernel<<<dim3(tiles_x * tiles_y, nl), kInterThreads, 0, st>>>(descs, g, tiles_x);
         }
         if (G > 1) CK(cudaEventRecord(e->ev_mc[gi], st));
         if (dbf) {

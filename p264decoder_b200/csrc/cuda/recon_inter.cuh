@@ -5,28 +5,26 @@
 // p264_frame_filter (core/mc.c:172-266,409-451), motion_compensation_chroma (core/mc.c:303-334)
 // and the inter branch of p264_macroblock_decode (decoder/macroblock.c:832-890).
 //
-// Work decomposition: a CTA owns kMbPerCta consecutive macroblocks of one lane.  Threads
-// [0, 16*kMbPerCta) each own one luma 4x4 block, threads [16*kMbPerCta, 24*kMbPerCta) one chroma
-// 4x4 block (four 2x2 MC cells).  Every sample depends only on its own 4x4 block's (ref, mv), so
-// no partition walk is needed.
-//
-// v2 (instruction-bound in v1, DRAM traffic already == algorithmic bytes):
-//  * the CTA's 128 luma blocks are counting-sorted by interpolation class (copy / H only / V only /
-//    diagonal / centre) so that a warp runs one class and skips the filter stages it does not need
-//    with warp-uniform branches instead of paying for the union of all 16 phases;
-//  * 6-tap filters are byte dot products: horizontal taps = 2 x dp4a on funnel-shifted words, vertical
-//    taps = byte transpose (PRMT) + 2 x dp4a, centre taps = dp2a on packed 16-bit intermediates; the
-//    +16 rounding rides in the dp4a accumulator, which also absorbs the centre's +512 exactly
-//    (sum of taps = 32, 32 * 16 = 512);
-//  * chroma bilinear samples are one PRMT + one dp4a each.
+// v3 work decomposition (v1/v2 were ALU-issue bound on per-thread bookkeeping, not on filter math):
+//  * a CTA owns a tile of 8x4 macroblocks (128x64 luma samples) of one lane; the 32 macroblock
+//    records are staged in shared memory once (coalesced 16-byte loads);
+//  * the tile's 512 luma 4x4 blocks are bucketed by interpolation class (copy / H / V / diagonal /
+//    centre+b / centre+h) with warp-aggregated shared-memory counters, so a warp runs ONE
+//    class-specialised, straight-line filter body (template parameter, no per-thread selects);
+//  * predictions go to a shared-memory picture tile; blocks that carry residual are compacted into a
+//    second list so dequant + inverse transform runs with full warps, on the tile;
+//  * the finished tile leaves with 16-byte (luma) / 8-byte (chroma) coalesced stores.
+//  Filter arithmetic: 6-tap filters are byte dot products (dp4a on funnel-shifted words for the
+//  horizontal taps, byte transpose + dp4a for the vertical taps, dp2a on packed 16-bit intermediates
+//  for the centre), +16 / +512 rounding rides in the accumulators (32 * 16 = 512 exactly).
 #pragma once
 #include "common.cuh"
 
 namespace p264b200 {
 
-constexpr int kMbPerCta = 8;
-constexpr int kLumaThreads = 16 * kMbPerCta;
-constexpr int kInterThreads = 24 * kMbPerCta;
+constexpr int kTileW = 8, kTileH = 4;          // macroblocks per CTA tile
+constexpr int kTileMbs = kTileW * kTileH;
+constexpr int kInterThreads = 256;
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 {
@@ -66,145 +64,199 @@ __device__ __forceinline__ int tap6_bytes(uint32_t w0, uint32_t w1, uint32_t w2,
     return dp4a_us(b, kTapB, dp4a_us(a, kTapA, acc));
 }
 
-// 12 consecutive samples starting at p (any alignment) as three packed words
-__device__ __forceinline__ void load_row12(const uint8_t *p, uint32_t &a, uint32_t &b, uint32_t &c)
+// A block's window starts at byte `base + sh/8`; base is 4-byte aligned and the row stride is a
+// multiple of 4, so one (aligned pointer, shift) pair serves every row.
+struct RowPtr {
+    const uint32_t *w;  // aligned word holding the first window byte of row 0
+    int sh;             // 8 * (byte offset inside that word)
+    int stride4;        // row stride in 32-bit words
+};
+__device__ __forceinline__ RowPtr row_ptr(const uint8_t *p, int stride)
 {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~uintptr_t(3));
-    const int sh = (int)(addr & 3) * 8;
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-    a = __funnelshift_r(w0, w1, sh);
-    b = __funnelshift_r(w1, w2, sh);
-    c = __funnelshift_r(w2, w3, sh);
+    RowPtr r;
+    r.w = reinterpret_cast<const uint32_t *>(addr & ~uintptr_t(3));
+    r.sh = (int)(addr & 3) * 8;
+    r.stride4 = stride >> 2;
+    return r;
 }
-// 8 consecutive samples (enough for the vertical filter's 4 columns at x or x+1)
-__device__ __forceinline__ void load_row8(const uint8_t *p, uint32_t &a, uint32_t &b)
+// 9 window bytes of row r (enough for four 6-tap outputs) as a, b and byte 0 of c
+__device__ __forceinline__ void load_win9(const RowPtr &rp, int r, uint32_t &a, uint32_t &b, uint32_t &c)
 {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~uintptr_t(3));
-    const int sh = (int)(addr & 3) * 8;
+    const uint32_t *w = rp.w + r * rp.stride4;
     const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-    a = __funnelshift_r(w0, w1, sh);
-    b = __funnelshift_r(w1, w2, sh);
+    a = __funnelshift_r(w0, w1, rp.sh);
+    b = __funnelshift_r(w1, w2, rp.sh);
+    c = w2 >> rp.sh;
+}
+// 4 window bytes of row r
+__device__ __forceinline__ uint32_t load_win4(const RowPtr &rp, int r)
+{
+    const uint32_t *w = rp.w + r * rp.stride4;
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), rp.sh);
 }
 __device__ __forceinline__ int byte_of(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xff); }
 
-// interpolation class of a quarter-pel phase: 0 copy, 1 horizontal only, 2 vertical only,
-// 3 diagonal (b and h, no centre), 4 centre j involved
+// interpolation class of a quarter-pel phase:
+//   0 copy, 1 horizontal only, 2 vertical only, 3 diagonal (b and h, no centre),
+//   4 centre j (+ b when fy is odd), fx == 2,  5 centre j + h, fy == 2 and fx odd
+enum { kMcCopy = 0, kMcH = 1, kMcV = 2, kMcDiag = 3, kMcCentreB = 4, kMcCentreH = 5, kMcClasses = 6 };
 __device__ __forceinline__ int mc_class(int fx, int fy)
 {
-    if (fx == 0) return fy == 0 ? 0 : 2;
-    if (fy == 0) return 1;
-    return (fx == 2 || fy == 2) ? 4 : 3;
+    if (fx == 0) return fy == 0 ? kMcCopy : kMcV;
+    if (fy == 0) return kMcH;
+    if (fx == 2) return kMcCentreB;
+    return fy == 2 ? kMcCentreH : kMcDiag;
 }
 
-// Quarter-pel luma prediction of one 4x4 block.  `src` points at the integer sample the MV's
-// integer part selects (already clamped into the padded plane).  H.264 8.4.2.2.1 with the
-// reference's rounding points: b,h = clip((tap+16)>>5), j = clip((tap(tap)+512)>>10),
-// quarter positions = (s1+s2+1)>>1 of the two neighbours mc_luma picks (core/mc.c:244-257).
-// Stages are skipped per warp (the caller groups threads by class), never per thread.
-__device__ __forceinline__ void mc_luma_4x4(const uint8_t *__restrict__ src, int stride, int fx, int fy, uint32_t out[4])
+// four packed rows of vertical half samples h = clip((tapV + 16) >> 5) from the 9 window rows vc[0..8]
+// (4 columns each): byte transpose, then two dp4a down each column
+__device__ __forceinline__ void vfilter4(const uint32_t vc[9], uint32_t hw[4])
+{
+    uint32_t col[4][2];
+#pragma unroll
+    for (int g4 = 0; g4 < 2; g4++) {
+        const uint32_t t0 = __byte_perm(vc[4 * g4 + 0], vc[4 * g4 + 1], 0x5140), t1 = __byte_perm(vc[4 * g4 + 2], vc[4 * g4 + 3], 0x5140);
+        const uint32_t t2 = __byte_perm(vc[4 * g4 + 0], vc[4 * g4 + 1], 0x7362), t3 = __byte_perm(vc[4 * g4 + 2], vc[4 * g4 + 3], 0x7362);
+        col[0][g4] = __byte_perm(t0, t1, 0x5410);
+        col[1][g4] = __byte_perm(t0, t1, 0x7632);
+        col[2][g4] = __byte_perm(t2, t3, 0x5410);
+        col[3][g4] = __byte_perm(t2, t3, 0x7632);
+    }
+    int hq[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t tail = byte_of(vc[8], c);  // row 8 of this column
+#pragma unroll
+        for (int r = 0; r < 4; r++) hq[r][c] = tap6_bytes(col[c][0], col[c][1], tail, r, 16) >> 5;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) hw[r] = pack4_sat_u8(hq[r][0], hq[r][1], hq[r][2], hq[r][3]);
+}
+
+// four packed rows of centre samples j = clip((tapV(tapH) + 512) >> 10) from the 9x4 horizontal
+// intermediates hm (each already + 16): two rows per dp2a
+__device__ __forceinline__ void centre4(const int hm[9][4], uint32_t jw[4])
+{
+    int jq[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int pk[4];  // rows (0,1) (2,3) (4,5) (6,7) as s16x2
+#pragma unroll
+        for (int k = 0; k < 4; k++) pk[k] = (int)__byte_perm((uint32_t)hm[2 * k][c], (uint32_t)hm[2 * k + 1][c], 0x5410);
+        const int j0 = dp2a_lo_ss(pk[2], kTapB, dp2a_hi_ss(pk[1], kTapA, dp2a_lo_ss(pk[0], kTapA, 0)));
+        const int j2 = dp2a_lo_ss(pk[3], kTapB, dp2a_hi_ss(pk[2], kTapA, dp2a_lo_ss(pk[1], kTapA, 0)));
+        const int j1 = dp2a_hi_ss(pk[3], kTapOdd1, dp2a_lo_ss(pk[2], kTapOdd1, dp2a_hi_ss(pk[1], kTapOdd0, dp2a_lo_ss(pk[0], kTapOdd0, 0))));
+        const int j3 = dp2a_hi_ss(hm[8][c], kTapOdd1, dp2a_lo_ss(pk[3], kTapOdd1, dp2a_hi_ss(pk[2], kTapOdd0, dp2a_lo_ss(pk[1], kTapOdd0, 0))));
+        jq[0][c] = j0 >> 10;
+        jq[1][c] = j1 >> 10;
+        jq[2][c] = j2 >> 10;
+        jq[3][c] = j3 >> 10;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) jw[r] = pack4_sat_u8(jq[r][0], jq[r][1], jq[r][2], jq[r][3]);
+}
+
+// Quarter-pel luma prediction of one 4x4 block, specialised per interpolation class.  `src` points at
+// the integer sample the MV's integer part selects (already clamped into the padded plane).
+// H.264 8.4.2.2.1 with the reference's rounding points: b,h = clip((tap+16)>>5),
+// j = clip((tap(tap)+512)>>10), quarter positions = (s1+s2+1)>>1 of the two neighbours mc_luma picks
+// (core/mc.c:244-257).  (fx, fy) must belong to class CLS.
+template <int CLS>
+__device__ __forceinline__ void mc_luma_cls(const uint8_t *__restrict__ src, int stride, int fx, int fy, uint32_t out[4])
 {
     const int dx = fx == 3, dy = fy == 3;
-    const bool need_h = fx != 0, need_v = fy != 0;
-    const bool need_j = need_h && need_v && (fx == 2 || fy == 2);
-    const unsigned am = __activemask();
-    const bool w_h = __any_sync(am, need_h), w_v = __any_sync(am, need_v), w_j = __any_sync(am, need_j);
-
-    // window rows 0..8 = picture rows -2..6, words: a = cols -2..1, b = cols 2..5, c = cols 6..9
-    uint32_t wa[9], wb[9], wc[9];
+    if (CLS == kMcCopy) {
+        const RowPtr rp = row_ptr(src, stride);
 #pragma unroll
-    for (int r = 0; r < 9; r++) {
-        wa[r] = wb[r] = wc[r] = 0;
-        const bool row_needed = w_v || (r >= 2 && r <= 5);
-        if (row_needed) {
-            if (w_h)
-                load_row12(src + (r - 2) * stride - 2, wa[r], wb[r], wc[r]);
-            else
-                load_row8(src + (r - 2) * stride - 2, wa[r], wb[r]);
+        for (int r = 0; r < 4; r++) out[r] = load_win4(rp, r);
+    } else if (CLS == kMcH) {
+        // b on rows 0..3; quarter phases average with G (fx 1) or G(x+1) (fx 3)
+        const RowPtr rp = row_ptr(src - 2, stride);
+        const int gsh = 16 + 8 * dx;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t a, b, c;
+            load_win9(rp, r, a, b, c);
+            const uint32_t bw = pack4_sat_u8(tap6_bytes(a, b, c, 0, 16) >> 5, tap6_bytes(a, b, c, 1, 16) >> 5,
+                                             tap6_bytes(a, b, c, 2, 16) >> 5, tap6_bytes(a, b, c, 3, 16) >> 5);
+            const uint32_t gw = __funnelshift_r(a, b, gsh);
+            out[r] = avg4_u8(bw, fx == 2 ? bw : gw);
+        }
+    } else if (CLS == kMcV) {
+        // h on columns 0..3; quarter phases average with G (fy 1) or G(y+1) (fy 3)
+        const RowPtr rp = row_ptr(src - 2 * stride, stride);
+        uint32_t vc[9], hw[4];
+#pragma unroll
+        for (int r = 0; r < 9; r++) vc[r] = load_win4(rp, r);
+        vfilter4(vc, hw);
+#pragma unroll
+        for (int r = 0; r < 4; r++) out[r] = avg4_u8(hw[r], fy == 2 ? hw[r] : (dy ? vc[r + 3] : vc[r + 2]));
+    } else if (CLS == kMcDiag) {
+        // (b at row y + dy, h at column x + dx) averaged
+        const RowPtr rp = row_ptr(src - 2 * stride - 2, stride);
+        const int csh = 16 + 8 * dx;
+        uint32_t vc[9], bw[5], hw[4];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            uint32_t a, b, c;
+            load_win9(rp, r, a, b, c);
+            vc[r] = __funnelshift_r(a, b, csh);
+            if (r >= 2 && r <= 6)
+                bw[r - 2] = pack4_sat_u8(tap6_bytes(a, b, c, 0, 16) >> 5, tap6_bytes(a, b, c, 1, 16) >> 5,
+                                         tap6_bytes(a, b, c, 2, 16) >> 5, tap6_bytes(a, b, c, 3, 16) >> 5);
+        }
+        vfilter4(vc, hw);
+#pragma unroll
+        for (int r = 0; r < 4; r++) out[r] = avg4_u8(dy ? bw[r + 1] : bw[r], hw[r]);
+    } else {
+        // centre: horizontal intermediates of all 9 rows, j down the columns
+        const RowPtr rp = row_ptr(src - 2 * stride - 2, stride);
+        const int csh = 16 + 8 * dx;
+        int hm[9][4];
+        uint32_t vc[9], jw[4];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            uint32_t a, b, c;
+            load_win9(rp, r, a, b, c);
+            if (CLS == kMcCentreH) vc[r] = __funnelshift_r(a, b, csh);
+#pragma unroll
+            for (int k = 0; k < 4; k++) hm[r][k] = tap6_bytes(a, b, c, k, 16);
+        }
+        centre4(hm, jw);
+        if (CLS == kMcCentreB) {
+            // fx == 2: j alone (fy 2) or averaged with b of row y (fy 1) / y+1 (fy 3)
+            uint32_t bw[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) bw[r] = pack4_sat_u8(hm[r + 2][0] >> 5, hm[r + 2][1] >> 5, hm[r + 2][2] >> 5, hm[r + 2][3] >> 5);
+#pragma unroll
+            for (int r = 0; r < 4; r++) out[r] = avg4_u8(jw[r], fy == 2 ? jw[r] : (dy ? bw[r + 1] : bw[r]));
+        } else {
+            // fy == 2, fx odd: j averaged with h of column x (fx 1) / x+1 (fx 3)
+            uint32_t hw[4];
+            vfilter4(vc, hw);
+#pragma unroll
+            for (int r = 0; r < 4; r++) out[r] = avg4_u8(jw[r], hw[r]);
         }
     }
+}
 
-    // horizontal 6-tap + 16 for the rows in use: all 9 for the centre, rows 2..6 otherwise
-    int hm[9][4];
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        const bool row_needed = w_h && (w_j || (r >= 2 && r <= 6 && (w_v || r <= 5)));
-#pragma unroll
-        for (int c = 0; c < 4; c++) hm[r][c] = row_needed ? tap6_bytes(wa[r], wb[r], wc[r], c, 16) : 0;
+// class dispatch (warp-uniform when the caller buckets blocks by class)
+__device__ __forceinline__ void mc_luma_dispatch(int cls, const uint8_t *__restrict__ src, int stride, int fx, int fy, uint32_t out[4])
+{
+    switch (cls) {
+    case kMcCopy: mc_luma_cls<kMcCopy>(src, stride, fx, fy, out); break;
+    case kMcH: mc_luma_cls<kMcH>(src, stride, fx, fy, out); break;
+    case kMcV: mc_luma_cls<kMcV>(src, stride, fx, fy, out); break;
+    case kMcDiag: mc_luma_cls<kMcDiag>(src, stride, fx, fy, out); break;
+    case kMcCentreB: mc_luma_cls<kMcCentreB>(src, stride, fx, fy, out); break;
+    default: mc_luma_cls<kMcCentreH>(src, stride, fx, fy, out); break;
     }
-
-    // vertical half samples h at column x (or x+1): transpose the 9x4 byte block, then dp4a down each column
-    uint32_t hw[4] = {0, 0, 0, 0};  // packed rows of h
-    if (w_v) {
-        int hq[4][4];
-        uint32_t vc[9];
-#pragma unroll
-        for (int r = 0; r < 9; r++) vc[r] = __funnelshift_r(wa[r], wb[r], 8 * (2 + dx));
-        uint32_t col[4][2];
-#pragma unroll
-        for (int g4 = 0; g4 < 2; g4++) {
-            const uint32_t t0 = __byte_perm(vc[4 * g4 + 0], vc[4 * g4 + 1], 0x5140), t1 = __byte_perm(vc[4 * g4 + 2], vc[4 * g4 + 3], 0x5140);
-            const uint32_t t2 = __byte_perm(vc[4 * g4 + 0], vc[4 * g4 + 1], 0x7362), t3 = __byte_perm(vc[4 * g4 + 2], vc[4 * g4 + 3], 0x7362);
-            col[0][g4] = __byte_perm(t0, t1, 0x5410);
-            col[1][g4] = __byte_perm(t0, t1, 0x7632);
-            col[2][g4] = __byte_perm(t2, t3, 0x5410);
-            col[3][g4] = __byte_perm(t2, t3, 0x7632);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t tail = byte_of(vc[8], c);  // row 8 of this column
-#pragma unroll
-            for (int r = 0; r < 4; r++) hq[r][c] = tap6_bytes(col[c][0], col[c][1], tail, r, 16) >> 5;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) hw[r] = pack4_sat_u8(hq[r][0], hq[r][1], hq[r][2], hq[r][3]);
-    }
-
-    // centre samples j: 6-tap down the (already +16) horizontal intermediates, two rows per dp2a
-    uint32_t jw[4] = {0, 0, 0, 0};  // packed rows of j
-    if (w_j) {
-        int jq[4][4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int pk[4];  // rows (0,1) (2,3) (4,5) (6,7) as s16x2
-#pragma unroll
-            for (int k = 0; k < 4; k++) pk[k] = (int)__byte_perm((uint32_t)hm[2 * k][c], (uint32_t)hm[2 * k + 1][c], 0x5410);
-            const int j0 = dp2a_lo_ss(pk[2], kTapB, dp2a_hi_ss(pk[1], kTapA, dp2a_lo_ss(pk[0], kTapA, 0)));
-            const int j2 = dp2a_lo_ss(pk[3], kTapB, dp2a_hi_ss(pk[2], kTapA, dp2a_lo_ss(pk[1], kTapA, 0)));
-            const int j1 = dp2a_hi_ss(pk[3], kTapOdd1, dp2a_lo_ss(pk[2], kTapOdd1, dp2a_hi_ss(pk[1], kTapOdd0, dp2a_lo_ss(pk[0], kTapOdd0, 0))));
-            const int j3 = dp2a_hi_ss(hm[8][c], kTapOdd1, dp2a_lo_ss(pk[3], kTapOdd1, dp2a_hi_ss(pk[2], kTapOdd0, dp2a_lo_ss(pk[1], kTapOdd0, 0))));
-            jq[0][c] = j0 >> 10;
-            jq[1][c] = j1 >> 10;
-            jq[2][c] = j2 >> 10;
-            jq[3][c] = j3 >> 10;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) jw[r] = pack4_sat_u8(jq[r][0], jq[r][1], jq[r][2], jq[r][3]);
-    }
-
-    // quarter positions: rounded average of the two samples mc_luma would pick (core/mc.c:244-257),
-    // on packed rows; the operand choice depends only on the phase
-    const bool x_is_j = need_j, x_is_b = need_h && !need_j, x_is_h = !need_h && need_v;
-    const bool y_is_g = (need_h != need_v) && (((need_h ? fx : fy) & 1) != 0);
-    const bool y_is_b = need_j && fx == 2 && fy != 2, y_is_h = need_h && need_v && fx != 2 && (fy == 2 || !need_j);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        // integer sample: G, G(x+1) for fx==3 & fy==0, G(y+1) for fy==3 & fx==0
-        const uint32_t grow_a = (dy && fx == 0) ? wa[r + 3] : wa[r + 2];
-        const uint32_t grow_b = (dy && fx == 0) ? wb[r + 3] : wb[r + 2];
-        const uint32_t gw = __funnelshift_r(grow_a, grow_b, 8 * (2 + ((dx && fy == 0) ? 1 : 0)));
-        uint32_t bw = 0;
-        if (w_h) {
-            const int *hr = dy ? hm[r + 3] : hm[r + 2];
-            bw = pack4_sat_u8((dy ? hm[r + 3][0] : hm[r + 2][0]) >> 5, (dy ? hm[r + 3][1] : hm[r + 2][1]) >> 5,
-                              (dy ? hm[r + 3][2] : hm[r + 2][2]) >> 5, (dy ? hm[r + 3][3] : hm[r + 2][3]) >> 5);
-            (void)hr;
-        }
-        const uint32_t X = x_is_j ? jw[r] : x_is_b ? bw : x_is_h ? hw[r] : gw;
-        const uint32_t Y = y_is_g ? gw : y_is_b ? bw : y_is_h ? hw[r] : X;
-        out[r] = avg4_u8(X, Y);
-    }
+}
+// any phase (the one-block table shims in blockops.cu)
+__device__ __forceinline__ void mc_luma_4x4(const uint8_t *__restrict__ src, int stride, int fx, int fy, uint32_t out[4])
+{
+    mc_luma_dispatch(mc_class(fx, fy), src, stride, fx, fy, out);
 }
 
 // eighth-pel bilinear chroma prediction of one 2x2 cell (core/mc.c:303-334): one dp4a per sample
@@ -225,122 +277,227 @@ __device__ __forceinline__ void mc_chroma_2x2(const uint8_t *__restrict__ src, i
         o[r * 2 + 1] = dp4a_uu(__byte_perm(row[r], row[r + 1], 0x6521), wgt, 32) >> 6;
     }
 }
+// a 4x4 chroma block whose four 2x2 cells share one MV: 5 rows x 5 samples, one dp4a per sample
+__device__ __forceinline__ void mc_chroma_4x4(const uint8_t *__restrict__ src, int stride, int dx, int dy, uint32_t out[4])
+{
+    const uint32_t wgt = (uint32_t)((8 - dx) * (8 - dy)) | ((uint32_t)(dx * (8 - dy)) << 8) | ((uint32_t)((8 - dx) * dy) << 16) |
+                         ((uint32_t)(dx * dy) << 24);
+    const RowPtr rp = row_ptr(src, stride);
+    uint32_t lo[5], hi[5];  // samples 0..3 and 1..4 of each row
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t *w = rp.w + r * rp.stride4;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+        lo[r] = __funnelshift_r(w0, w1, rp.sh);
+        hi[r] = __funnelshift_r(lo[r], w1 >> rp.sh, 8);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int v[4];
+        // sample c: bytes (A, B, C, D) = (row r col c, row r col c+1, row r+1 col c, row r+1 col c+1)
+        v[0] = dp4a_uu(__byte_perm(lo[r], lo[r + 1], 0x5410), wgt, 32) >> 6;
+        v[1] = dp4a_uu(__byte_perm(lo[r], lo[r + 1], 0x6521), wgt, 32) >> 6;
+        v[2] = dp4a_uu(__byte_perm(lo[r], lo[r + 1], 0x7632), wgt, 32) >> 6;
+        v[3] = dp4a_uu(__byte_perm(hi[r], hi[r + 1], 0x7632), wgt, 32) >> 6;
+        out[r] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    }
+}
 
 #ifdef P264B200_DEFINE_KERNELS
-__global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g)
+struct InterSmem {
+    p264b200_mb mb[kTileMbs];                       // the tile's macroblock records
+    uint8_t y[16 * kTileH][16 * kTileW];            // picture tile, luma
+    uint8_t c[2][8 * kTileH][8 * kTileW];           // picture tile, Cb / Cr
+    uint16_t perm[16 * kTileMbs];                   // luma blocks bucketed by class: block | class << 12
+    uint16_t res[24 * kTileMbs];                    // blocks that carry residual: luma block, or 512 + chroma block
+    const uint8_t *ref[kMaxRefs][3];
+    int cnt[8];                                     // blocks per class
+    int nres;
+};
+
+__global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x)
 {
-    constexpr int kKeys = 11;           // (coded ? 0 : 5) + class, 10 = nothing to do
-    __shared__ int s_cnt[4][12];        // [luma warp][key], then exclusive start of (key, warp)
-    __shared__ uint8_t s_perm[kLumaThreads];
+    __shared__ __align__(16) InterSmem sm;
     const FrameDesc &fd = descs[blockIdx.y];
     if (fd.slice_type != P264B200_SLICE_P) return;
-    const int n_mb = g.mb_w * g.mb_h;
-    const int tid = threadIdx.x;
-    const bool luma = tid < kLumaThreads;
-    const int mb_base = blockIdx.x * kMbPerCta;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1;
+    const int mbx0 = (blockIdx.x % tiles_x) * kTileW, mby0 = (blockIdx.x / tiles_x) * kTileH;
 
-    // ---- counting sort of the CTA's luma blocks by (has residual, interpolation class): a warp then
-    // runs one filter class, and the dequant/IDCT code only runs in the warps that hold coded blocks
-    int key = kKeys - 1, rank = 0;
-    const int lane = tid & 31, wid = tid >> 5;
-    if (luma) {
-        const int mb_xy = mb_base + (tid >> 4), b = tid & 15;
-        if (mb_xy < n_mb) {
-            const p264b200_mb &m = fd.mbs[mb_xy];
-            if (!P264B200_IS_INTRA(m.mb_type))
-                key = mc_class(m.mv[b][0] & 3, m.mv[b][1] & 3) + ((m.luma_mask >> b & 1) ? 0 : 5);
+    // ---- stage the tile's macroblock records (6 x 16 bytes each); outside the picture = "intra" = skipped
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.mb);
+        const uint4 *src = reinterpret_cast<const uint4 *>(fd.mbs);
+        for (int i = tid; i < kTileMbs * 6; i += kInterThreads) {
+            const int mb = i / 6, part = i - 6 * mb;
+            const int mbx = mbx0 + (mb & (kTileW - 1)), mby = mby0 + (mb / kTileW);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (mbx < g.mb_w && mby < g.mb_h) v = __ldg(src + (size_t)(mby * g.mb_w + mbx) * 6 + part);
+            dst[i] = v;
         }
-        int cnt = 0;
-#pragma unroll
-        for (int c = 0; c < kKeys; c++) {
-            const unsigned msk = __ballot_sync(0xffffffffu, key == c);
-            if (key == c) rank = __popc(msk & ((1u << lane) - 1));
-            if (lane == c) cnt = __popc(msk);
-        }
-        if (lane < kKeys) s_cnt[wid][lane] = cnt;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        // exclusive prefix over (key major, warp minor), 44 entries handled by lanes 0..10
-        int c4[4] = {0, 0, 0, 0}, tot = 0;
-        if (lane < kKeys) {
-#pragma unroll
-            for (int w2 = 0; w2 < 4; w2++) c4[w2] = s_cnt[w2][lane], tot += c4[w2];
-        }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        int base = incl - tot;
-        if (lane < kKeys) {
-#pragma unroll
-            for (int w2 = 0; w2 < 4; w2++) s_cnt[w2][lane] = base, base += c4[w2];
+        if (tid < 8) sm.cnt[tid] = 0;
+        if (tid == 8) sm.nres = 0;
+        if (tid >= 32 && tid < 32 + 3 * kMaxRefs) {
+            const int k = tid - 32;
+            sm.ref[k / 3][k % 3] = (k / 3) < fd.num_ref ? fd.ref[k / 3][k % 3] : nullptr;
         }
     }
     __syncthreads();
-    if (luma) s_perm[s_cnt[wid][key] + rank] = (uint8_t)tid;
+
+    // ---- bucket the 512 luma blocks by interpolation class, compact the blocks with residual
+    int my_key[2], my_pos[2];
+#pragma unroll
+    for (int rd = 0; rd < 3; rd++) {
+        const int k = tid + kInterThreads * rd;  // rd 0,1: luma block k; rd 2: chroma block k - 512
+        const p264b200_mb &m = sm.mb[rd < 2 ? (k >> 4) : (tid >> 3)];
+        const bool inter = !P264B200_IS_INTRA(m.mb_type);
+        bool coded;
+        if (rd < 2) {
+            const int b = k & 15;
+            const int key = inter ? mc_class(m.mv[b][0] & 3, m.mv[b][1] & 3) : 7;
+            coded = inter && (m.luma_mask >> b & 1);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sm.cnt[key], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            my_key[rd] = key;
+            my_pos[rd] = base + __popc(peers & lt);
+        } else {
+            coded = inter && m.cbp_chroma != 0;
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, coded);
+        if (cm) {
+            const int leader = __ffs(cm) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&sm.nres, __popc(cm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (coded) sm.res[base + __popc(cm & lt)] = (uint16_t)k;
+        }
+    }
+    __syncthreads();
+    int start[kMcClasses + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int c = 0; c < kMcClasses; c++) start[c + 1] = start[c] + sm.cnt[c];
+#pragma unroll
+    for (int rd = 0; rd < 2; rd++) {
+        int s0 = 0;
+#pragma unroll
+        for (int c = 1; c < kMcClasses; c++) s0 = my_key[rd] == c ? start[c] : s0;
+        if (my_key[rd] < kMcClasses) sm.perm[s0 + my_pos[rd]] = (uint16_t)((tid + kInterThreads * rd) | (my_key[rd] << 12));
+    }
+    const int n_items = start[kMcClasses];
     __syncthreads();
 
-    if (luma) {
-        const int item = s_perm[tid];
-        const int mb_xy = mb_base + (item >> 4), b = item & 15;
-        if (mb_xy >= n_mb) return;
-        const p264b200_mb &m = fd.mbs[mb_xy];
-        if (P264B200_IS_INTRA(m.mb_type)) return;
-        const int mbx = mb_xy % g.mb_w, mby = mb_xy / g.mb_w;
-        const int bx = b & 3, by = b >> 2;
-        const int ref = mb_ref8(m, b);
+    // ---- luma prediction, one class per warp (up to the bucket boundaries)
+#pragma unroll 1
+    for (int rd = 0; rd < 2; rd++) {
+        const int idx = tid + kInterThreads * rd;
+        if (idx >= n_items) break;
+        const int e = sm.perm[idx], cls = e >> 12, k = e & 511;
+        const int mb = k >> 4, b = k & 15, bx = b & 3, by = b >> 2;
+        const p264b200_mb &m = sm.mb[mb];
+        const int lx = 16 * (mb & (kTileW - 1)) + 4 * bx, ly = 16 * (mb / kTileW) + 4 * by;  // position inside the tile
         const int mvx = m.mv[b][0], mvy = m.mv[b][1];
         // integer position, clamped so the 9x9 window (plus word alignment slack) stays inside
         // the 32-sample border; beyond the clamp every tap sees replicated edge samples anyway
-        const int x0 = clip3i(16 * mbx + 4 * bx + (mvx >> 2), -16, g.width + 8);
-        const int y0 = clip3i(16 * mby + 4 * by + (mvy >> 2), -16, g.height + 8);
+        const int x0 = clip3i(16 * mbx0 + lx + (mvx >> 2), -16, g.width + 8);
+        const int y0 = clip3i(16 * mby0 + ly + (mvy >> 2), -16, g.height + 8);
         uint32_t px[4];
-        mc_luma_4x4(fd.ref[ref][0] + (ptrdiff_t)y0 * g.y_stride + x0, g.y_stride, mvx & 3, mvy & 3, px);
-        if (m.luma_mask >> b & 1) {
-            const int idx = __popc(m.luma_mask & ((1u << b) - 1));
-            residual4x4(fd.coefs + m.coef_off + 16 * idx, m.qp, false, 0, px);
-        }
-        uint8_t *dst = fd.cur[0] + (ptrdiff_t)(16 * mby + 4 * by) * g.y_stride + 16 * mbx + 4 * bx;
+        mc_luma_dispatch(cls, sm.ref[mb_ref8(m, b)][0] + (ptrdiff_t)y0 * g.y_stride + x0, g.y_stride, mvx & 3, mvy & 3, px);
 #pragma unroll
-        for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(dst + r * g.y_stride) = px[r];
-    } else {
-        const int mb_xy = mb_base + ((tid - kLumaThreads) >> 3);
-        if (mb_xy >= n_mb) return;
-        const p264b200_mb &m = fd.mbs[mb_xy];
-        if (P264B200_IS_INTRA(m.mb_type)) return;
-        const int mbx = mb_xy % g.mb_w, mby = mb_xy / g.mb_w;
-        const int cb = (tid - kLumaThreads) & 7, plane = 1 + (cb >> 2), i = cb & 3;
-        const int cx = i & 1, cy = i >> 1;  // 4x4 chroma block inside the 8x8
-        uint32_t px[4] = {0, 0, 0, 0};
+        for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(&sm.y[ly + r][lx]) = px[r];
+    }
+
+    // ---- chroma prediction: thread = one 4x4 chroma block = one luma 8x8 quadrant's motion
+    {
+        const int mb = tid >> 3, cb = tid & 7, plane = cb >> 2, i = cb & 3;
+        const p264b200_mb &m = sm.mb[mb];
+        if (!P264B200_IS_INTRA(m.mb_type)) {
+            const int cx = i & 1, cy = i >> 1;  // 4x4 chroma block inside the 8x8
+            const int lx = 8 * (mb & (kTileW - 1)) + 4 * cx, ly = 8 * (mb / kTileW) + 4 * cy;
+            const int lb0 = 8 * cy + 2 * cx;  // top-left luma 4x4 block of the quadrant
+            const uint8_t *rplane = sm.ref[m.ref[2 * cy + cx]][1 + plane];
+            const int2 v0 = *reinterpret_cast<const int2 *>(m.mv[lb0]), v1 = *reinterpret_cast<const int2 *>(m.mv[lb0 + 4]);
+            uint32_t px[4];
+            if (v0.x == v0.y && v0.x == v1.x && v0.x == v1.y) {
+                const int mvx = (short)(v0.x & 0xffff), mvy = v0.x >> 16;
+                const int x0 = clip3i(8 * mbx0 + lx + (mvx >> 3), -8, g.width / 2 + 4);
+                const int y0 = clip3i(8 * mby0 + ly + (mvy >> 3), -8, g.height / 2 + 4);
+                mc_chroma_4x4(rplane + (ptrdiff_t)y0 * g.c_stride + x0, g.c_stride, mvx & 7, mvy & 7, px);
+            } else {
+                px[0] = px[1] = px[2] = px[3] = 0;
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-            // 2x2 cell s of this chroma block <-> luma 4x4 block (2cx + s&1, 2cy + s>>1)
-            const int lb = (2 * cy + (s >> 1)) * 4 + 2 * cx + (s & 1);
-            const int ref = mb_ref8(m, lb);
-            const int mvx = m.mv[lb][0], mvy = m.mv[lb][1];
-            const int x0 = clip3i(8 * mbx + 4 * cx + 2 * (s & 1) + (mvx >> 3), -8, g.width / 2 + 4);
-            const int y0 = clip3i(8 * mby + 4 * cy + 2 * (s >> 1) + (mvy >> 3), -8, g.height / 2 + 4);
-            int o[4];
-            mc_chroma_2x2(fd.ref[ref][plane] + (ptrdiff_t)y0 * g.c_stride + x0, g.c_stride, mvx & 7, mvy & 7, o);
-            const int r0 = 2 * (s >> 1), c0 = 2 * (s & 1);
-            px[r0] |= (uint32_t)(o[0] | (o[1] << 8)) << (8 * c0);
-            px[r0 + 1] |= (uint32_t)(o[2] | (o[3] << 8)) << (8 * c0);
+                for (int s = 0; s < 4; s++) {
+                    // 2x2 cell s of this chroma block <-> luma 4x4 block lb0 + (s&1) + 4*(s>>1)
+                    const int lb = lb0 + (s & 1) + 4 * (s >> 1);
+                    const int mvx = m.mv[lb][0], mvy = m.mv[lb][1];
+                    const int x0 = clip3i(8 * mbx0 + lx + 2 * (s & 1) + (mvx >> 3), -8, g.width / 2 + 4);
+                    const int y0 = clip3i(8 * mby0 + ly + 2 * (s >> 1) + (mvy >> 3), -8, g.height / 2 + 4);
+                    int o[4];
+                    mc_chroma_2x2(rplane + (ptrdiff_t)y0 * g.c_stride + x0, g.c_stride, mvx & 7, mvy & 7, o);
+                    const int r0 = 2 * (s >> 1), c0 = 2 * (s & 1);
+                    px[r0] |= (uint32_t)(o[0] | (o[1] << 8)) << (8 * c0);
+                    px[r0 + 1] |= (uint32_t)(o[2] | (o[3] << 8)) << (8 * c0);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(&sm.c[plane][ly + r][lx]) = px[r];
         }
-        if (m.cbp_chroma) {
+    }
+    __syncthreads();
+
+    // ---- residual on the tile: only blocks that carry coefficients (chroma: every block of an MB with cbp)
+    const int nres = sm.nres;
+#pragma unroll 1
+    for (int idx = tid; idx < nres; idx += kInterThreads) {
+        const int k = sm.res[idx];
+        uint32_t px[4];
+        if (k < 16 * kTileMbs) {
+            const int mb = k >> 4, b = k & 15;
+            const p264b200_mb &m = sm.mb[mb];
+            uint8_t *t = &sm.y[16 * (mb / kTileW) + 4 * (b >> 2)][16 * (mb & (kTileW - 1)) + 4 * (b & 3)];
+#pragma unroll
+            for (int r = 0; r < 4; r++) px[r] = *reinterpret_cast<const uint32_t *>(t + r * 16 * kTileW);
+            residual4x4(fd.coefs + m.coef_off + 16 * __popc(m.luma_mask & ((1u << b) - 1)), m.qp, false, 0, px);
+#pragma unroll
+            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(t + r * 16 * kTileW) = px[r];
+        } else {
+            const int q = k - 16 * kTileMbs, mb = q >> 3, cb = q & 7, plane = cb >> 2, i = cb & 3;
+            const p264b200_mb &m = sm.mb[mb];
+            uint8_t *t = &sm.c[plane][8 * (mb / kTileW) + 4 * (i >> 1)][8 * (mb & (kTileW - 1)) + 4 * (i & 1)];
+#pragma unroll
+            for (int r = 0; r < 4; r++) px[r] = *reinterpret_cast<const uint32_t *>(t + r * 8 * kTileW);
             const int qpc = c_chroma_qp[clip3i(m.qp + fd.chroma_qp_off, 0, 51)];
             const int16_t *cf = fd.coefs + m.coef_off + 16 * __popc(m.luma_mask);
             int dc[4];
-            chroma_dc(cf + 4 * (plane - 1), qpc, dc);
+            chroma_dc(cf + 4 * plane, qpc, dc);
             const int16_t *ac = nullptr;
             if (m.chroma_mask >> cb & 1) ac = cf + 8 + 16 * __popc(m.chroma_mask & ((1u << cb) - 1));
             residual4x4(ac, qpc, true, dc[i], px);
-        }
-        uint8_t *dst = fd.cur[plane] + (ptrdiff_t)(8 * mby + 4 * cy) * g.c_stride + 8 * mbx + 4 * cx;
 #pragma unroll
-        for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(dst + r * g.c_stride) = px[r];
+            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(t + r * 8 * kTileW) = px[r];
+        }
+    }
+    __syncthreads();
+
+    // ---- the tile leaves with coalesced stores; intra / outside macroblocks are not ours
+#pragma unroll
+    for (int rd = 0; rd < 2; rd++) {
+        const int i = tid + kInterThreads * rd, row = i >> 3, seg = i & 7;  // 64 rows x 8 macroblock-wide segments
+        const int mb = (row >> 4) * kTileW + seg;
+        if (!P264B200_IS_INTRA(sm.mb[mb].mb_type))
+            *reinterpret_cast<uint4 *>(fd.cur[0] + (ptrdiff_t)(16 * mby0 + row) * g.y_stride + 16 * (mbx0 + seg)) =
+                *reinterpret_cast<const uint4 *>(&sm.y[row][16 * seg]);
+    }
+#pragma unroll
+    for (int plane = 0; plane < 2; plane++) {
+        const int row = tid >> 3, seg = tid & 7;  // 32 rows x 8 segments of 8 samples
+        const int mb = (row >> 3) * kTileW + seg;
+        if (!P264B200_IS_INTRA(sm.mb[mb].mb_type))
+            *reinterpret_cast<uint2 *>(fd.cur[1 + plane] + (ptrdiff_t)(8 * mby0 + row) * g.c_stride + 8 * (mbx0 + seg)) =
+                *reinterpret_cast<const uint2 *>(&sm.c[plane][row][8 * seg]);
     }
 }
 #endif  // P264B200_DEFINE_KERNELS
