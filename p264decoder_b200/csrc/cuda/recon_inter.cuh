@@ -9,7 +9,7 @@
 //  * a CTA owns a tile of 8x4 macroblocks (128x64 luma samples) of one lane; the 32 macroblock
 //    records are staged in shared memory once (coalesced 16-byte loads);
 //  * the tile's 512 luma 4x4 blocks are bucketed by interpolation class (copy / H / V / diagonal /
-//    centre+b / centre+h) with warp-aggregated shared-memory counters, so a warp runs ONE
+//    centre+b / centre+h) with shared-memory counters, so a warp runs ONE
 //    class-specialised, straight-line filter body (template parameter, no per-thread selects);
 //  * predictions go to a shared-memory picture tile; blocks that carry residual are compacted into a
 //    second list so dequant + inverse transform runs with full warps, on the tile;
@@ -309,10 +309,12 @@ struct InterSmem {
     uint8_t y[16 * kTileH][16 * kTileW];            // picture tile, luma
     uint8_t c[2][8 * kTileH][8 * kTileW];           // picture tile, Cb / Cr
     uint16_t perm[16 * kTileMbs];                   // luma blocks bucketed by class: block | class << 12
-    uint16_t res[24 * kTileMbs];                    // blocks that carry residual: luma block, or 512 + chroma block
+    uint16_t cperm[8 * kTileMbs];                   // chroma blocks: one-MV quadrants from the front, per-cell MVs from the back
+    uint16_t res[24 * kTileMbs];                    // residual work: full blocks (luma: block, chroma: 512 + block) from the
+                                                    //   front, DC-only chroma blocks from the back
     const uint8_t *ref[kMaxRefs][3];
-    int cnt[8];                                     // blocks per class
-    int nres;
+    int cnt[8];                                     // [0..5] luma blocks per class, [6] one-MV chroma blocks, [7] per-cell chroma blocks
+    int nres[2];                                    // full / DC-only residual blocks
 };
 
 __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x)
@@ -320,59 +322,56 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
     __shared__ __align__(16) InterSmem sm;
     const FrameDesc &fd = descs[blockIdx.y];
     if (fd.slice_type != P264B200_SLICE_P) return;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt = (1u << lane) - 1;
+    const int tid = threadIdx.x;
     const int mbx0 = (blockIdx.x % tiles_x) * kTileW, mby0 = (blockIdx.x / tiles_x) * kTileH;
 
     // ---- stage the tile's macroblock records (6 x 16 bytes each); outside the picture = "intra" = skipped
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.mb);
-        const uint4 *src = reinterpret_cast<const uint4 *>(fd.mbs);
-        for (int i = tid; i < kTileMbs * 6; i += kInterThreads) {
-            const int mb = i / 6, part = i - 6 * mb;
-            const int mbx = mbx0 + (mb & (kTileW - 1)), mby = mby0 + (mb / kTileW);
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (mbx < g.mb_w && mby < g.mb_h) v = __ldg(src + (size_t)(mby * g.mb_w + mbx) * 6 + part);
-            dst[i] = v;
-        }
-        if (tid < 8) sm.cnt[tid] = 0;
-        if (tid == 8) sm.nres = 0;
-        if (tid >= 32 && tid < 32 + 3 * kMaxRefs) {
-            const int k = tid - 32;
-            sm.ref[k / 3][k % 3] = (k / 3) < fd.num_ref ? fd.ref[k / 3][k % 3] : nullptr;
-        }
+    if (tid < kTileMbs * 6) {
+        const int ly = tid / (6 * kTileW), rest = tid - ly * (6 * kTileW);  // one tile row = 8 consecutive records
+        const int mbx = mbx0 + rest / 6, mby = mby0 + ly;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (mbx < g.mb_w && mby < g.mb_h) v = __ldg(reinterpret_cast<const uint4 *>(fd.mbs + (size_t)mby * g.mb_w + mbx0) + rest);
+        reinterpret_cast<uint4 *>(sm.mb)[tid] = v;
+    } else if (tid < kTileMbs * 6 + 3 * kMaxRefs) {
+        const int k = tid - kTileMbs * 6, r = k / 3;
+        sm.ref[r][k - 3 * r] = r < fd.num_ref ? fd.ref[r][k - 3 * r] : nullptr;
+    } else if (tid < kTileMbs * 6 + 3 * kMaxRefs + 8) {
+        sm.cnt[tid - (kTileMbs * 6 + 3 * kMaxRefs)] = 0;
+        if (tid == kTileMbs * 6 + 3 * kMaxRefs) sm.nres[0] = sm.nres[1] = 0;
     }
     __syncthreads();
 
-    // ---- bucket the 512 luma blocks by interpolation class, compact the blocks with residual
+    // ---- bucket the 512 luma blocks by interpolation class and the 256 chroma blocks by "one MV for the whole
+    // quadrant"; list the blocks that carry residual.  Shared-memory atomics: one instruction per block.
     int my_key[2], my_pos[2];
 #pragma unroll
-    for (int rd = 0; rd < 3; rd++) {
-        const int k = tid + kInterThreads * rd;  // rd 0,1: luma block k; rd 2: chroma block k - 512
-        const p264b200_mb &m = sm.mb[rd < 2 ? (k >> 4) : (tid >> 3)];
-        const bool inter = !P264B200_IS_INTRA(m.mb_type);
-        bool coded;
-        if (rd < 2) {
-            const int b = k & 15;
-            const int key = inter ? mc_class(m.mv[b][0] & 3, m.mv[b][1] & 3) : 7;
-            coded = inter && (m.luma_mask >> b & 1);
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&sm.cnt[key], __popc(peers));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            my_key[rd] = key;
-            my_pos[rd] = base + __popc(peers & lt);
-        } else {
-            coded = inter && m.cbp_chroma != 0;
+    for (int rd = 0; rd < 2; rd++) {
+        const int k = tid + kInterThreads * rd, b = k & 15;
+        const p264b200_mb &m = sm.mb[k >> 4];
+        my_key[rd] = 7;
+        if (!P264B200_IS_INTRA(m.mb_type)) {
+            const int mv = *reinterpret_cast<const int *>(m.mv[b]);
+            my_key[rd] = mc_class(mv & 3, (mv >> 16) & 3);
+            my_pos[rd] = atomicAdd(&sm.cnt[my_key[rd]], 1);
+            if (m.luma_mask >> b & 1) sm.res[atomicAdd(&sm.nres[0], 1)] = (uint16_t)k;
         }
-        const unsigned cm = __ballot_sync(0xffffffffu, coded);
-        if (cm) {
-            const int leader = __ffs(cm) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&sm.nres, __popc(cm));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (coded) sm.res[base + __popc(cm & lt)] = (uint16_t)k;
+    }
+    {
+        const int mb = tid >> 3, cb = tid & 7, i = cb & 3;
+        const p264b200_mb &m = sm.mb[mb];
+        if (!P264B200_IS_INTRA(m.mb_type)) {
+            const int lb0 = 8 * (i >> 1) + 2 * (i & 1);
+            const int2 v0 = *reinterpret_cast<const int2 *>(m.mv[lb0]), v1 = *reinterpret_cast<const int2 *>(m.mv[lb0 + 4]);
+            if (v0.x == v0.y && v0.x == v1.x && v0.x == v1.y)
+                sm.cperm[atomicAdd(&sm.cnt[6], 1)] = (uint16_t)tid;
+            else
+                sm.cperm[8 * kTileMbs - 1 - atomicAdd(&sm.cnt[7], 1)] = (uint16_t)tid;
+            if (m.cbp_chroma) {
+                if (m.chroma_mask >> cb & 1)
+                    sm.res[atomicAdd(&sm.nres[0], 1)] = (uint16_t)(16 * kTileMbs + tid);
+                else
+                    sm.res[24 * kTileMbs - 1 - atomicAdd(&sm.nres[1], 1)] = (uint16_t)tid;
+            }
         }
     }
     __syncthreads();
@@ -410,19 +409,22 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
         for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(&sm.y[ly + r][lx]) = px[r];
     }
 
-    // ---- chroma prediction: thread = one 4x4 chroma block = one luma 8x8 quadrant's motion
+    // ---- chroma prediction: item = one 4x4 chroma block = one luma 8x8 quadrant's motion
     {
-        const int mb = tid >> 3, cb = tid & 7, plane = cb >> 2, i = cb & 3;
-        const p264b200_mb &m = sm.mb[mb];
-        if (!P264B200_IS_INTRA(m.mb_type)) {
+        const int n_one = sm.cnt[6], n_cell = sm.cnt[7];
+        const bool one = tid < n_one;
+        // one-MV quadrants fill the list (= the warps) from the front, per-cell quadrants from the back
+        if (one || tid >= 8 * kTileMbs - n_cell) {
+            const int q = sm.cperm[tid];
+            const int mb = q >> 3, cb = q & 7, plane = cb >> 2, i = cb & 3;
+            const p264b200_mb &m = sm.mb[mb];
             const int cx = i & 1, cy = i >> 1;  // 4x4 chroma block inside the 8x8
             const int lx = 8 * (mb & (kTileW - 1)) + 4 * cx, ly = 8 * (mb / kTileW) + 4 * cy;
             const int lb0 = 8 * cy + 2 * cx;  // top-left luma 4x4 block of the quadrant
             const uint8_t *rplane = sm.ref[m.ref[2 * cy + cx]][1 + plane];
-            const int2 v0 = *reinterpret_cast<const int2 *>(m.mv[lb0]), v1 = *reinterpret_cast<const int2 *>(m.mv[lb0 + 4]);
             uint32_t px[4];
-            if (v0.x == v0.y && v0.x == v1.x && v0.x == v1.y) {
-                const int mvx = (short)(v0.x & 0xffff), mvy = v0.x >> 16;
+            if (one) {
+                const int mvx = m.mv[lb0][0], mvy = m.mv[lb0][1];
                 const int x0 = clip3i(8 * mbx0 + lx + (mvx >> 3), -8, g.width / 2 + 4);
                 const int y0 = clip3i(8 * mby0 + ly + (mvy >> 3), -8, g.height / 2 + 4);
                 mc_chroma_4x4(rplane + (ptrdiff_t)y0 * g.c_stride + x0, g.c_stride, mvx & 7, mvy & 7, px);
@@ -448,36 +450,59 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
     }
     __syncthreads();
 
-    // ---- residual on the tile: only blocks that carry coefficients (chroma: every block of an MB with cbp)
-    const int nres = sm.nres;
+    // ---- residual on the tile: blocks with coefficients get dequant + inverse transform ...
+    const int nres = sm.nres[0], ndc = sm.nres[1];
 #pragma unroll 1
     for (int idx = tid; idx < nres; idx += kInterThreads) {
         const int k = sm.res[idx];
-        uint32_t px[4];
-        if (k < 16 * kTileMbs) {
-            const int mb = k >> 4, b = k & 15;
-            const p264b200_mb &m = sm.mb[mb];
-            uint8_t *t = &sm.y[16 * (mb / kTileW) + 4 * (b >> 2)][16 * (mb & (kTileW - 1)) + 4 * (b & 3)];
-#pragma unroll
-            for (int r = 0; r < 4; r++) px[r] = *reinterpret_cast<const uint32_t *>(t + r * 16 * kTileW);
-            residual4x4(fd.coefs + m.coef_off + 16 * __popc(m.luma_mask & ((1u << b) - 1)), m.qp, false, 0, px);
-#pragma unroll
-            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(t + r * 16 * kTileW) = px[r];
+        const bool chroma = k >= 16 * kTileMbs;
+        const int q = k & (16 * kTileMbs - 1);
+        const int mb = chroma ? q >> 3 : q >> 4;
+        const p264b200_mb &m = sm.mb[mb];
+        const int tmx = mb & (kTileW - 1), tmy = mb / kTileW;
+        uint8_t *t;
+        int pitch, qp, dcv = 0;
+        const int16_t *lvl;
+        if (!chroma) {
+            const int b = q & 15;
+            t = &sm.y[16 * tmy + 4 * (b >> 2)][16 * tmx + 4 * (b & 3)];
+            pitch = 16 * kTileW;
+            qp = m.qp;
+            lvl = fd.coefs + m.coef_off + 16 * __popc(m.luma_mask & ((1u << b) - 1));
         } else {
-            const int q = k - 16 * kTileMbs, mb = q >> 3, cb = q & 7, plane = cb >> 2, i = cb & 3;
-            const p264b200_mb &m = sm.mb[mb];
-            uint8_t *t = &sm.c[plane][8 * (mb / kTileW) + 4 * (i >> 1)][8 * (mb & (kTileW - 1)) + 4 * (i & 1)];
-#pragma unroll
-            for (int r = 0; r < 4; r++) px[r] = *reinterpret_cast<const uint32_t *>(t + r * 8 * kTileW);
-            const int qpc = c_chroma_qp[clip3i(m.qp + fd.chroma_qp_off, 0, 51)];
+            const int cb = q & 7, plane = cb >> 2, i = cb & 3;
+            t = &sm.c[plane][8 * tmy + 4 * (i >> 1)][8 * tmx + 4 * (i & 1)];
+            pitch = 8 * kTileW;
+            qp = c_chroma_qp[clip3i(m.qp + fd.chroma_qp_off, 0, 51)];
             const int16_t *cf = fd.coefs + m.coef_off + 16 * __popc(m.luma_mask);
             int dc[4];
-            chroma_dc(cf + 4 * plane, qpc, dc);
-            const int16_t *ac = nullptr;
-            if (m.chroma_mask >> cb & 1) ac = cf + 8 + 16 * __popc(m.chroma_mask & ((1u << cb) - 1));
-            residual4x4(ac, qpc, true, dc[i], px);
+            chroma_dc(cf + 4 * plane, qp, dc);
+            dcv = i == 0 ? dc[0] : i == 1 ? dc[1] : i == 2 ? dc[2] : dc[3];
+            lvl = cf + 8 + 16 * __popc(m.chroma_mask & ((1u << cb) - 1));
+        }
+        uint32_t px[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(t + r * 8 * kTileW) = px[r];
+        for (int r = 0; r < 4; r++) px[r] = *reinterpret_cast<const uint32_t *>(t + r * pitch);
+        residual4x4(lvl, qp, chroma, dcv, px);
+#pragma unroll
+        for (int r = 0; r < 4; r++) *reinterpret_cast<uint32_t *>(t + r * pitch) = px[r];
+    }
+    // ---- ... chroma blocks with a DC term only add the constant (dc + 32) >> 6 (what add4x4_idct makes of a lone DC)
+#pragma unroll 1
+    for (int idx = tid; idx < ndc; idx += kInterThreads) {
+        const int q = sm.res[24 * kTileMbs - 1 - idx];
+        const int mb = q >> 3, cb = q & 7, plane = cb >> 2, i = cb & 3;
+        const p264b200_mb &m = sm.mb[mb];
+        uint8_t *t = &sm.c[plane][8 * (mb / kTileW) + 4 * (i >> 1)][8 * (mb & (kTileW - 1)) + 4 * (i & 1)];
+        const int qpc = c_chroma_qp[clip3i(m.qp + fd.chroma_qp_off, 0, 51)];
+        int dc[4];
+        chroma_dc(fd.coefs + m.coef_off + 16 * __popc(m.luma_mask) + 4 * plane, qpc, dc);
+        const int r0 = ((i == 0 ? dc[0] : i == 1 ? dc[1] : i == 2 ? dc[2] : dc[3]) + 32) >> 6;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t p = *reinterpret_cast<const uint32_t *>(t + r * 8 * kTileW);
+            *reinterpret_cast<uint32_t *>(t + r * 8 * kTileW) =
+                pack4_sat_u8((int)(p & 0xff) + r0, (int)((p >> 8) & 0xff) + r0, (int)((p >> 16) & 0xff) + r0, (int)(p >> 24) + r0);
         }
     }
     __syncthreads();
