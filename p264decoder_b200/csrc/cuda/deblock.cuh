@@ -5,24 +5,28 @@
 // edges then horizontal edges per macroblock; MB(x,y) therefore depends on MB(x-1,y) (whole MB)
 // and on MB(x+1,y-1) (its left-edge filter rewrites columns 13..15 of MB(x,y-1), which MB(x,y)'s
 // top-edge filter reads).  A picture-wide "all vertical, then all horizontal" pass is NOT
-// bit-exact, so the kernel keeps the reference order: row y may filter MB x once row y-1 has
-// published progress >= min(x+2, mb_w).
+// bit-exact, so the kernel keeps the reference order as a two-macroblock-lag row wavefront.
 //
-// Work decomposition (v2).  Luma and chroma are independent given the boundary strengths, so
-// they run as separate warps with separate progress flags.  A warp owns one macroblock row of
-// TWO lanes (streams): threads 0..15 work on stream 2p, threads 16..31 on stream 2p+1, always in
-// the same code path, so there is no luma/chroma divergence and every thread is busy:
-//   luma warp  : thread = one of the 16 lines crossing the edge direction
-//   chroma warp: thread = one of the 8 Cb + 8 Cr lines
-// Vertical edges (filter along a row) are done entirely in registers: the thread keeps its row of
-// the current macroblock (one 128-bit load) plus the 4 right-most samples of the previous
-// macroblock, carried from iteration to iteration.  Horizontal edges need the transpose, which
-// goes through a small shared-memory tile (row-wise 32-bit stores, column-wise byte loads, both
-// bank-conflict free).  Boundary strengths are derived one per thread and exchanged with warp
-// shuffles.  Only samples that changed are written back; the right-most 4 columns stay in
-// registers until the next macroblock's left edge has been filtered.
+// Work decomposition (v3; v2 spent 40 % of its issue slots spinning on shared-memory flags and most of
+// the rest on one-sample-per-register arithmetic and byte shuffling):
+//  * TWO sample lines per register: every tap (p3..q3) is held as s16x2, the filters are the packed
+//    forms in swar.cuh (VABSDIFF4 / VIADD.16 / VIMNMX.S16x2 / VIADDMNMX.RELU), so one thread filters
+//    two rows (vertical edges) or two columns (horizontal edges) per instruction stream;
+//  * a warp owns one macroblock row of FOUR lanes (streams): 8 threads per stream, always in the
+//    same code path.  Luma and chroma are independent given the boundary strengths and run as
+//    separate warps (role = CTA) with separate progress flags;
+//  * a CTA owns kDbfRows consecutive macroblock rows and runs them in LOCKSTEP: one __syncthreads per
+//    macroblock step, warp w works on macroblock (step - 2w).  Waiting warps sit in the barrier
+//    instead of polling.  The four sample rows that cross a row boundary are handed down through a
+//    small shared-memory ring; only every kDbfRows-th row boundary goes through global memory
+//    (progress word + acquire/release), polled by one thread, one macroblock ahead of need;
+//  * vertical edges are filtered in registers straight from two 16-byte row loads; the transpose for
+//    the horizontal edges is a shared-memory tile written as rows and read as 16-bit column pairs;
+//  * all global traffic is full 16-byte (luma) / 8-byte (chroma) rows: a macroblock's rows are stored
+//    once, after the next macroblock's left edge has finalised their last three columns.
 #pragma once
 #include "common.cuh"
+#include "swar.cuh"
 
 namespace p264b200 {
 
@@ -86,106 +90,6 @@ __device__ __forceinline__ void dbf_chroma(int v[4], int alpha, int beta, int bs
     }
 }
 
-// ---- branch-free (predicated) forms used by the frame kernel ----------------------------------
-// one luma edge on a line held in registers; bs == 0 leaves the line untouched
-__device__ __forceinline__ void luma_edge(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3, int bs,
-                                          int alpha, int beta, uint32_t tc0_packed, bool any_strong)
-{
-    const int tc0 = (int)((tc0_packed >> (8 * ((bs - 1) & 3))) & 0xff);
-    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-    const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-    const bool fn = f && bs < 4;
-    const int avg = (p0 + q0 + 1) >> 1;
-    const int np1 = p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0);
-    const int nq1 = q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0);
-    const int tc = tc0 + (int)ap + (int)aq;
-    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-    int r1 = (fn && ap) ? np1 : p1, r0 = fn ? clip8i(p0 + delta) : p0;
-    int s0 = fn ? clip8i(q0 - delta) : q0, s1 = (fn && aq) ? nq1 : q1;
-    int r2 = p2, s2 = q2;
-    if (any_strong) {  // warp-uniform: some line of this edge is an intra macroblock edge
-        const bool fs = f && bs == 4;
-        const bool sm = abs(p0 - q0) < ((alpha >> 2) + 2);
-        const bool sp = fs && sm && ap, sq = fs && sm && aq;
-        const int wp0 = (2 * p1 + p0 + q1 + 2) >> 2, wq0 = (2 * q1 + q0 + p1 + 2) >> 2;
-        r0 = fs ? (sp ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : wp0) : r0;
-        r1 = sp ? (p2 + p1 + p0 + q0 + 2) >> 2 : r1;
-        r2 = sp ? (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3 : r2;
-        s0 = fs ? (sq ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : wq0) : s0;
-        s1 = sq ? (p0 + q0 + q1 + q2 + 2) >> 2 : s1;
-        s2 = sq ? (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3 : s2;
-    }
-    p2 = r2, p1 = r1, p0 = r0, q0 = s0, q1 = s1, q2 = s2;
-}
-__device__ __forceinline__ void chroma_edge(int p1, int &p0, int &q0, int q1, int bs, int alpha, int beta, uint32_t tc0_packed)
-{
-    const int tc = (int)((tc0_packed >> (8 * ((bs - 1) & 3))) & 0xff) + 1;
-    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-    const int n0 = bs < 4 ? clip8i(p0 + delta) : (2 * p1 + p0 + q1 + 2) >> 2;
-    const int m0 = bs < 4 ? clip8i(q0 - delta) : (2 * q1 + q0 + p1 + 2) >> 2;
-    p0 = f ? n0 : p0;
-    q0 = f ? m0 : q0;
-}
-
-// packed-parameter variants (see DeblockSide)
-__device__ __forceinline__ void luma_edge_p(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3, int bs,
-                                            uint32_t prm, bool any_strong)
-{
-    const int alpha = prm & 0xff, beta = (prm >> 8) & 31;
-    const int tc0 = (int)((prm >> (8 + 5 * bs)) & 31) & (bs < 4 ? 31 : 0);
-    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-    const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-    const bool fn = f && bs < 4;
-    const int avg = (p0 + q0 + 1) >> 1;
-    const int np1 = p1 + clip3i(((p2 + avg) >> 1) - p1, -tc0, tc0);
-    const int nq1 = q1 + clip3i(((q2 + avg) >> 1) - q1, -tc0, tc0);
-    const int tc = tc0 + (int)ap + (int)aq;
-    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-    int r1 = (fn && ap) ? np1 : p1, r0 = fn ? clip8i(p0 + delta) : p0;
-    int s0 = fn ? clip8i(q0 - delta) : q0, s1 = (fn && aq) ? nq1 : q1;
-    int r2 = p2, s2 = q2;
-    if (any_strong) {  // warp-uniform: some line of this edge is an intra macroblock edge
-        const bool fs = f && bs == 4;
-        const bool sm = abs(p0 - q0) < ((alpha >> 2) + 2);
-        const bool sp = fs && sm && ap, sq = fs && sm && aq;
-        const int wp0 = (2 * p1 + p0 + q1 + 2) >> 2, wq0 = (2 * q1 + q0 + p1 + 2) >> 2;
-        r0 = fs ? (sp ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : wp0) : r0;
-        r1 = sp ? (p2 + p1 + p0 + q0 + 2) >> 2 : r1;
-        r2 = sp ? (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3 : r2;
-        s0 = fs ? (sq ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : wq0) : s0;
-        s1 = sq ? (p0 + q0 + q1 + q2 + 2) >> 2 : s1;
-        s2 = sq ? (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3 : s2;
-    }
-    p2 = r2, p1 = r1, p0 = r0, q0 = s0, q1 = s1, q2 = s2;
-}
-__device__ __forceinline__ void chroma_edge_p(int p1, int &p0, int &q0, int q1, int bs, uint32_t prm)
-{
-    const int alpha = prm & 0xff, beta = (prm >> 8) & 31;
-    const int tc = (int)((prm >> (8 + 5 * bs)) & 31) + 1;
-    const bool f = bs != 0 && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-    const int delta = clip3i((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
-    const int n0 = bs < 4 ? clip8i(p0 + delta) : (2 * p1 + p0 + q1 + 2) >> 2;
-    const int m0 = bs < 4 ? clip8i(q0 - delta) : (2 * q1 + q0 + p1 + 2) >> 2;
-    p0 = f ? n0 : p0;
-    q0 = f ? m0 : q0;
-}
-
-// alpha / beta / packed tc0[3] for an averaged QP (core/frame.c:476-483)
-struct EdgeParams {
-    int alpha, beta;
-    uint32_t tc0;
-};
-__device__ __forceinline__ EdgeParams edge_params(int qp, int alpha_off, int beta_off)
-{
-    EdgeParams e;
-    const int ia = clip3i(qp + alpha_off, 0, 51);
-    e.alpha = c_alpha[ia];
-    e.beta = c_beta[clip3i(qp + beta_off, 0, 51)];
-    e.tc0 = *reinterpret_cast<const uint32_t *>(c_tc0[ia]);
-    return e;
-}
-
 // boundary strength of one 4-sample segment (core/frame.c:535-581); m = current MB, n = neighbour
 // across the edge (== m for inner edges)
 __device__ __forceinline__ int boundary_strength(const p264b200_mb *__restrict__ m, const p264b200_mb *__restrict__ n, int dir,
@@ -225,12 +129,6 @@ __device__ __forceinline__ uint32_t pack_edge_params(int qp, int alpha_off, int 
            ((uint32_t)c_tc0[ia][1] << 18) | ((uint32_t)c_tc0[ia][2] << 23);
 }
 
-constexpr int kLS = 20;                  // luma transpose tile: 20 rows (-4..15) x 16 cols, 20-byte rows
-constexpr int kLHalf = 20 * kLS + 16;    // bytes per stream half (+16 shifts the second half's banks)
-constexpr int kCS2 = 12;                 // chroma transpose tile: per plane 10 rows (-2..7) x 8 cols, 12-byte rows
-constexpr int kCPlane = 10 * kCS2 + 8;
-constexpr int kCHalf = 2 * kCPlane + 16;
-
 #ifdef P264B200_DEFINE_KERNELS
 
 // one thread per (macroblock, segment): 8 boundary strengths -> one word; thread seg 0 also writes the QP word
@@ -262,354 +160,273 @@ __global__ void __launch_bounds__(256) deblock_bs_kernel(const FrameDesc *__rest
     }
 }
 
-// A CTA owns kDbfRows consecutive macroblock rows (one warp each) of one stream pair and one role.
-// Inside the CTA the hand-off between row r and row r+1 (progress flag AND the four sample rows that
-// cross the boundary) goes through shared memory; only every kDbfRows-th row boundary uses the global
-// progress words + a device-scope fence.  A global hand-off costs several microseconds per macroblock
-// step (measured), a shared-memory one ~100 cycles, and the wavefront pays it on every step.
-constexpr int kDbfRows = 8;
-constexpr int kDbfRing = 8;  // macroblocks a producer row may run ahead of the slots its consumer still reads
+
+constexpr int kDbfRows = 8;     // macroblock rows (warps) per CTA
+constexpr int kDbfQuad = 4;     // lanes (streams) per warp, 8 threads each
+constexpr int kDbfRing = 4;     // hand-off slots per producer row (the consumer runs two macroblocks behind)
+constexpr int kDbfTile = 272;   // bytes per (warp, stream) transpose tile: 16 rows x 16 B, + 16 B bank skew
+constexpr int kDbfSlot = 80;    // bytes per (slot, stream): 4 rows x 16 B, + 16 B bank skew
 
 struct DbfSmem {
-    uint8_t tile[kDbfRows][2 * kLHalf];                 // per-warp transpose tiles
-    uint4 ring[kDbfRows][kDbfRing][2][4];               // [producer warp][slot][stream half][sample row 12..15] (luma)
-    volatile int progress[kDbfRows];                    // macroblocks finished by each warp
+    uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];              // luma: row r at 16r; chroma: plane p row r at 64p + 8r
+    uint8_t ring[kDbfRows][kDbfRing][kDbfQuad][kDbfSlot];    // luma: rows 12..15 at 16k; chroma: plane p rows 6,7 at 16p + 8k
+    uint8_t top0[kDbfQuad][kDbfSlot];                         // same layout: rows above warp 0, fetched from global memory
     int ticket;
 };
 
-__device__ __forceinline__ void wait_smem(volatile int *flag, int need, int lane)
+// one luma edge on two lines: v -> p3 p2 p1 p0 q0 q1 q2 q3
+__device__ __forceinline__ void dbf_luma_edge2(uint32_t *v, int bs, uint32_t prm, bool mb_edge)
 {
-    if (lane == 0) {
-        // exponential back-off: rows that have not started yet must not steal issue slots from working warps
-        int spins = 0;
-        while (*flag < need) __nanosleep(++spins < 64 ? 20 : 1000);
+    if (!__any_sync(0xffffffffu, bs != 0)) return;
+    const int alpha = prm & 0xff, beta = (prm >> 8) & 31, tc0 = (prm >> (8 + 5 * bs)) & 31;
+    const swar::EdgeK k = swar::edge_k((unsigned)(bs - 1) < 3u ? alpha : 0, beta, tc0);
+    swar::luma_normal(v[1], v[2], v[3], v[4], v[5], v[6], k);
+    if (mb_edge && __any_sync(0xffffffffu, bs == 4)) {
+        // intra macroblock edge: the strong filter replaces the (disabled) normal one on those lines
+        const swar::EdgeK k4 = swar::edge_k(bs == 4 ? alpha : 0, beta, 0);
+        swar::luma_strong(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], k4, alpha);
     }
-    __threadfence_block();
-    __syncwarp();
 }
-__device__ __forceinline__ void wait_global(const int *prog, int need, bool poll)
+// one chroma edge on two lines: v -> p1 p0 q0 q1
+__device__ __forceinline__ void dbf_chroma_edge2(uint32_t *v, int bs, uint32_t prm, bool mb_edge)
 {
-    if (poll) {
-        int spins = 0;
-        while (ld_acquire(prog) < need) __nanosleep(++spins < 32 ? 20 : 1000);
+    if (!__any_sync(0xffffffffu, bs != 0)) return;
+    const int alpha = prm & 0xff, beta = (prm >> 8) & 31, tc0 = (prm >> (8 + 5 * bs)) & 31;
+    const swar::EdgeK k = swar::edge_k(bs != 0 ? alpha : 0, beta, tc0);
+    uint32_t p0 = v[1], q0 = v[2];
+    swar::chroma_edge2(v[0], p0, q0, v[3], k, false);
+    if (mb_edge && __any_sync(0xffffffffu, bs == 4)) {
+        uint32_t sp0 = v[1], sq0 = v[2];
+        swar::chroma_edge2(v[0], sp0, sq0, v[3], k, true);
+        if (bs == 4) p0 = sp0, q0 = sq0;
     }
-    __syncwarp();
+    v[1] = p0, v[2] = q0;
 }
 
-struct RowCtx {
-    int w, row;
-    bool top_smem, top_glob, bottom_smem, bottom_glob;
-};
+template <int N> struct DbfVec;
+template <> struct DbfVec<4> { typedef uint4 type; };
+template <> struct DbfVec<2> { typedef uint2 type; };
+__device__ __forceinline__ void vec_get(const uint4 &v, uint32_t *r) { r[0] = v.x, r[1] = v.y, r[2] = v.z, r[3] = v.w; }
+__device__ __forceinline__ void vec_get(const uint2 &v, uint32_t *r) { r[0] = v.x, r[1] = v.y; }
+__device__ __forceinline__ void vec_set(uint4 &v, const uint32_t *r) { v = make_uint4(r[0], r[1], r[2], r[3]); }
+__device__ __forceinline__ void vec_set(uint2 &v, const uint32_t *r) { v = make_uint2(r[0], r[1]); }
 
-__device__ __forceinline__ int ub(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }  // byte k, zero-extended
-__device__ __forceinline__ uint32_t pk4(int a, int b, int c, int d) { return (uint32_t)(a | (b << 8) | (c << 16) | (d << 24)); }
-
-// shared-memory progress is counted in half macroblocks: 2x+1 = vertical edges of MB x done (so the
-// previous MB's columns 12..15 are final), 2x+2 = MB x done.  Row r+1 may filter the top edge of MB x as
-// soon as row r has finished the VERTICAL edges of MB x+1 -- a lag of 1.5 instead of 2 macroblocks.
-__device__ __forceinline__ void publish_smem(volatile int *flag, int v, int lane)
+// The macroblock rows of one CTA for one role.  C = false: luma (16 rows x 16 B per macroblock, 4 edges per
+// direction, 4 rows handed down); C = true: Cb and Cr (per plane 8 rows x 8 B, 2 edges, 2 rows handed down,
+// threads 0..3 of a stream on Cb, 4..7 on Cr).
+template <bool C>
+__device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
+                                             int grp)
 {
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) *flag = v;
-}
+    constexpr int NW = C ? 2 : 4;    // 32-bit words per sample row of a macroblock
+    constexpr int RB = 4 * NW;       // bytes per row
+    constexpr int NR = C ? 8 : 16;   // rows per plane
+    constexpr int TR = C ? 2 : 4;    // rows handed down to the macroblock row below (per plane)
+    constexpr int NP = 4 + 4 * NW;   // taps along a row incl. the 4 samples left of the macroblock
+    constexpr int NQ = TR + NR;      // taps down a column incl. the rows above
+    typedef typename DbfVec<NW>::type Vec;
+    using swar::prmt;
 
-// ------------------------------------------------------------------------------ luma rows
-__device__ __forceinline__ void deblock_luma_row(DbfSmem &sm, const RowCtx rc, const FrameDesc &fd, const Geometry &g, int half,
-                                                 int i, bool act)
-{
-    const int lane = threadIdx.x & 31, row = rc.row, w = rc.w;
-    uint8_t *T = sm.tile[w] + half * kLHalf;  // this half's tile, row r at T + (r + 4) * kLS
-    int *prog = fd.row_progress + g.mb_h;     // [1]: luma deblock wavefront (CTA boundaries only, in macroblocks)
-    uint8_t *grow = fd.cur[0] + (ptrdiff_t)(16 * row + i) * g.y_stride;  // this thread's sample row
-    uint8_t *gtop = fd.cur[0] + (ptrdiff_t)(16 * row - 4 + (i & 3)) * g.y_stride;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, t = lane & 7;
+    const int pl = C ? t >> 2 : 0, j = C ? t & 3 : t;  // plane; row pair (vertical edges) = column pair (horizontal edges)
+    const int row = grp * kDbfRows + w;
+    const bool row_ok = row < g.mb_h;
+    const bool has_top = row > 0;
+    const bool top_smem = w > 0, top_glob = w == 0 && has_top;
+    const bool bottom_smem = w + 1 < kDbfRows && row + 1 < g.mb_h;
+    const bool bottom_glob = !bottom_smem && row + 1 < g.mb_h;
+    const int stream = kDbfQuad * quad + sub;
+    const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
+    const bool act = row_ok && stream < n_lanes && fd.deblock != 0;
+    int *prog = descs[kDbfQuad * quad].row_progress + (C ? 2 : 1) * g.mb_h;  // one progress word per (quad, role, row)
+    const int stride = C ? g.c_stride : g.y_stride;
+    // this thread's two sample rows, and (threads 0..3) the row above it moves between global and shared memory:
+    // luma row -4 + t; chroma plane t >> 1, row -2 + (t & 1)
+    uint8_t *grow = fd.cur[C ? 1 + pl : 0] + (ptrdiff_t)(NR * row + 2 * j) * stride;
+    uint8_t *gtop = C ? fd.cur[1 + ((t >> 1) & 1)] + (ptrdiff_t)(NR * row - 2 + (t & 1)) * stride : fd.cur[0] + (ptrdiff_t)(NR * row - 4 + (t & 3)) * stride;
+    const int top_off = C ? 16 * ((t >> 1) & 1) + 8 * (t & 1) : 16 * (t & 3);  // of that row inside a slot
     const DeblockSide *side = fd.dbf_bs + (size_t)row * g.mb_w;
-    uint32_t left = 0;                        // columns -4..-1 of this row (previous MB's 12..15)
-    uint4 own = make_uint4(0, 0, 0, 0), prm = make_uint4(0, 0, 0, 0);
-    uint32_t bsw = 0;
-    if (act) {
-        own = __ldcg(reinterpret_cast<const uint4 *>(grow));
-        bsw = __ldg(&side[0].bs[i >> 2]);
-        prm = __ldg(reinterpret_cast<const uint4 *>(side[0].luma));
+    uint8_t *T = sm.tile[w][sub] + (C ? 64 * pl : 0);
+    // rows this thread stores itself / hands to the row below through the ring
+    const bool store_a = !(bottom_smem && 2 * j > NR - TR), store_b = !(bottom_smem && 2 * j + 1 > NR - TR);
+    const bool to_ring = bottom_smem && 2 * j >= NR - TR;
+    const int ring_off = (C ? 16 * pl : 0) + RB * (2 * j - (NR - TR));
+
+    uint32_t prev[2][NW], cur[2][NW], nxt[2][NW];
+    uint32_t bsw = 0, bsw_n = 0;
+    uint4 prm = make_uint4(0, 0, 0, 0), prm_n = prm;
+    Vec tnext;
+#pragma unroll
+    for (int k = 0; k < NW; k++) prev[0][k] = prev[1][k] = cur[0][k] = cur[1][k] = nxt[0][k] = nxt[1][k] = 0;
+    {
+        uint32_t z[4] = {0, 0, 0, 0};
+        vec_set(tnext, z);
     }
-    const bool poll_g = act && i == 0 && rc.top_glob;
-    // rows 13..15 are finished (and written) by the row below when it lives in this CTA
-    const bool mine = !(rc.bottom_smem && i >= 13);
-    const bool to_ring = rc.bottom_smem && i >= 12;
-    bool dirty_prev = false;  // the previous MB changed samples that are still only in `left`
+    if (act) {
+        vec_get(__ldcg(reinterpret_cast<const Vec *>(grow)), cur[0]);
+        vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + stride)), cur[1]);
+        bsw = __ldg(&side[0].bs[j >> (C ? 0 : 1)]);
+        prm = __ldg(reinterpret_cast<const uint4 *>(C ? side[0].chroma : side[0].luma));
+    }
+    int seen = 0;  // newest progress value of the row above (global hand-off only)
 
-    for (int mbx = 0; mbx < g.mb_w; mbx++) {
-        // ---- prefetch the next macroblock's row, strengths and parameters (no dependency on other rows)
-        uint4 nxt = make_uint4(0, 0, 0, 0), prm_n = make_uint4(0, 0, 0, 0);
-        uint32_t bsw_n = 0;
-        if (act && mbx + 1 < g.mb_w) {
-            nxt = __ldcg(reinterpret_cast<const uint4 *>(grow + 16 * (mbx + 1)));
-            bsw_n = __ldg(&side[mbx + 1].bs[i >> 2]);
-            prm_n = __ldg(reinterpret_cast<const uint4 *>(side[mbx + 1].luma));
+    const int n_steps = g.mb_w + 2 * (kDbfRows - 1);
+#pragma unroll 1
+    for (int s = 0; s < n_steps; s++) {
+        __syncthreads();
+        const int x = s - 2 * w;
+        if (x < 0 || x >= g.mb_w || !row_ok) continue;
+        const bool last = x == g.mb_w - 1;
+
+        // ---- rows above through global memory: one thread polls, one macroblock ahead of need, so that the
+        // fetch of the next macroblock's rows overlaps this macroblock's filtering
+        if (top_glob) {
+            const int need = min(x + 2, g.mb_w);
+            if (seen < need) {
+                if (lane == 0) {
+                    int spins = 0;
+                    while ((seen = ld_acquire(prog + row - 1)) < need) __nanosleep(++spins < 16 ? 40 : 400);
+                }
+                seen = __shfl_sync(0xffffffffu, seen, 0);
+            }
+            if (x == 0) {
+                if (act && t < 4) *reinterpret_cast<Vec *>(sm.top0[sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop));
+            }
+            if (act && t < 4 && !last) tnext = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (x + 1)));
         }
-        const uint32_t bv = bsw & 0x0f0f0f0fu, bh = (bsw >> 4) & 0x0f0f0f0fu;  // byte e = bS of edge e
-        const unsigned any_v = __ballot_sync(0xffffffffu, bv != 0), any_h = __ballot_sync(0xffffffffu, bh != 0);
+        // ---- prefetch the next macroblock's rows, strengths and parameters
+        if (act && !last) {
+            vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + RB * (x + 1))), nxt[0]);
+            vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + stride + RB * (x + 1))), nxt[1]);
+            bsw_n = __ldg(&side[x + 1].bs[j >> (C ? 0 : 1)]);
+            prm_n = __ldg(reinterpret_cast<const uint4 *>(C ? side[x + 1].chroma : side[x + 1].luma));
+        }
 
-        // ---- vertical edges: the whole row lives in registers, independent of the row above
-        int v[20];
+        // ---- vertical edges: taps of this thread's two rows, two rows per register
         {
-            const uint32_t wd[5] = {left, own.x, own.y, own.z, own.w};
+            uint32_t P[NP];
 #pragma unroll
-            for (int k = 0; k < 20; k++) v[k] = ub(wd[k >> 2], k & 3);
-        }
-        if (any_v) {
+            for (int wd = 0; wd < 1 + NW; wd++) {
+                const uint32_t wa = wd == 0 ? prev[0][NW - 1] : cur[0][wd - 1], wb = wd == 0 ? prev[1][NW - 1] : cur[1][wd - 1];
+                const uint32_t t01 = prmt(wa, wb, 0x5140), t23 = prmt(wa, wb, 0x7362);
+                P[4 * wd + 0] = prmt(t01, 0, 0x4140);
+                P[4 * wd + 1] = prmt(t01, 0, 0x4342);
+                P[4 * wd + 2] = prmt(t23, 0, 0x4140);
+                P[4 * wd + 3] = prmt(t23, 0, 0x4342);
+            }
+            if (C) {
+                dbf_chroma_edge2(P + 2, bsw & 0xf, prm.x, true);
+                dbf_chroma_edge2(P + 6, (bsw >> 16) & 0xf, prm.z, false);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int bs = (bv >> (8 * e)) & 0xff;
-                const unsigned need = __ballot_sync(0xffffffffu, bs != 0);
-                if (!need) continue;
-                const unsigned strong = __ballot_sync(0xffffffffu, bs == 4);
-                luma_edge_p(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3], v[4 * e + 4], v[4 * e + 5], v[4 * e + 6],
-                            v[4 * e + 7], bs, e == 0 ? prm.x : prm.z, strong != 0);
+                for (int e = 0; e < 4; e++) dbf_luma_edge2(P + 4 * e, (bsw >> (8 * e)) & 0xf, e == 0 ? prm.x : prm.z, e == 0);
+            }
+#pragma unroll
+            for (int wd = 0; wd < 1 + NW; wd++) {
+                const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
+                const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
+                if (wd == 0)
+                    prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
+                else
+                    cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
             }
         }
-        // columns -4..-1 are final now (the previous MB's horizontal edges were filtered already)
-        if (mbx > 0) {
-            const uint32_t lw = pk4(v[0], v[1], v[2], v[3]);
-            if (act && mine && (dirty_prev || any_v)) __stcg(reinterpret_cast<uint32_t *>(grow + 16 * mbx - 4), lw);
-            if (to_ring) reinterpret_cast<uint32_t *>(&sm.ring[w][(mbx - 1) % kDbfRing][half][i - 12])[3] = lw;
-        }
-        if (rc.bottom_smem) publish_smem(&sm.progress[w], 2 * mbx + 1, lane);
-        uint32_t r[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) r[k] = pk4(v[4 + 4 * k], v[5 + 4 * k], v[6 + 4 * k], v[7 + 4 * k]);
-
-        // ---- the rows above become readable once row-1 has done the vertical edges of the next macroblock
-        uint4 top = make_uint4(0, 0, 0, 0);
-        if (rc.top_smem) {
-            wait_smem(&sm.progress[w - 1], min(2 * mbx + 3, 2 * g.mb_w), lane);
-            if (i < 4) top = sm.ring[w - 1][mbx % kDbfRing][half][i];
-        } else {
-            wait_global(prog + row - 1, min(mbx + 2, g.mb_w), poll_g);
-            if (act && rc.top_glob && i < 4 && any_h) top = __ldcg(reinterpret_cast<const uint4 *>(gtop + 16 * mbx));
-        }
-        unsigned top_edge = 0;
-        if (any_h) {
-            // transpose through shared memory, horizontal edges, transpose back
-#pragma unroll
-            for (int k = 0; k < 4; k++) *reinterpret_cast<uint32_t *>(T + (i + 4) * kLS + 4 * k) = r[k];
-            if (i < 4) {
-                *reinterpret_cast<uint32_t *>(T + i * kLS + 0) = top.x;
-                *reinterpret_cast<uint32_t *>(T + i * kLS + 4) = top.y;
-                *reinterpret_cast<uint32_t *>(T + i * kLS + 8) = top.z;
-                *reinterpret_cast<uint32_t *>(T + i * kLS + 12) = top.w;
+        // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
+        if (x > 0) {
+            Vec va, vb;
+            vec_set(va, prev[0]);
+            vec_set(vb, prev[1]);
+            if (act && store_a) __stcg(reinterpret_cast<Vec *>(grow + RB * (x - 1)), va);
+            if (act && store_b) __stcg(reinterpret_cast<Vec *>(grow + stride + RB * (x - 1)), vb);
+            if (to_ring) {
+                uint8_t *slot = sm.ring[w][(x - 1) & (kDbfRing - 1)][sub] + ring_off;
+                *reinterpret_cast<Vec *>(slot) = va;
+                *reinterpret_cast<Vec *>(slot + RB) = vb;
             }
+        }
+        // ---- transpose through shared memory: rows in, 16-bit column pairs out
+        {
+            Vec va, vb;
+            vec_set(va, cur[0]);
+            vec_set(vb, cur[1]);
+            *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
+            *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
+        }
+        uint8_t *slot_top = (top_smem ? sm.ring[w - 1][x & (kDbfRing - 1)][sub] : sm.top0[sub]);
+        uint8_t *topp = slot_top + (C ? 16 * pl : 0);
+        __syncwarp();
+        {
+            uint32_t Q[NQ];
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                const uint8_t *src = k < TR ? topp + RB * k + 2 * j : T + RB * (k - TR) + 2 * j;
+                Q[k] = (k < TR && !has_top) ? 0u : prmt(*reinterpret_cast<const uint16_t *>(src), 0, 0x4140);
+            }
+            if (C) {
+                dbf_chroma_edge2(Q + 0, (bsw >> 4) & 0xf, prm.y, true);
+                dbf_chroma_edge2(Q + 4, (bsw >> 20) & 0xf, prm.z, false);
+                if (has_top) *reinterpret_cast<uint16_t *>(topp + RB * 1 + 2 * j) = (uint16_t)prmt(Q[1], 0, 0x4420);
+                *reinterpret_cast<uint16_t *>(T + RB * 0 + 2 * j) = (uint16_t)prmt(Q[2], 0, 0x4420);
+                *reinterpret_cast<uint16_t *>(T + RB * 3 + 2 * j) = (uint16_t)prmt(Q[5], 0, 0x4420);
+                *reinterpret_cast<uint16_t *>(T + RB * 4 + 2 * j) = (uint16_t)prmt(Q[6], 0, 0x4420);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) dbf_luma_edge2(Q + 4 * e, (bsw >> (8 * e + 4)) & 0xf, e == 0 ? prm.y : prm.z, e == 0);
+#pragma unroll
+                for (int k = 1; k < NQ - 1; k++) {
+                    uint8_t *dst = k < TR ? topp + RB * k + 2 * j : T + RB * (k - TR) + 2 * j;
+                    if (k >= TR || has_top) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)prmt(Q[k], 0, 0x4420);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- back to rows: these wait in registers for the next macroblock's left edge
+        vec_get(*reinterpret_cast<const Vec *>(T + RB * (2 * j)), prev[0]);
+        vec_get(*reinterpret_cast<const Vec *>(T + RB * (2 * j + 1)), prev[1]);
+        // the rows above are finished: luma rows -3..-1, chroma row -1 (rows -4 / -2 are only read)
+        if (has_top && act && t < 4 && (C ? (t & 1) : (t != 0)))
+            __stcg(reinterpret_cast<Vec *>(gtop + RB * x), *reinterpret_cast<const Vec *>(slot_top + top_off));
+        if (last) {
+            Vec va, vb;
+            vec_set(va, prev[0]);
+            vec_set(vb, prev[1]);
+            if (act && store_a) __stcg(reinterpret_cast<Vec *>(grow + RB * x), va);
+            if (act && store_b) __stcg(reinterpret_cast<Vec *>(grow + stride + RB * x), vb);
+            if (to_ring) {
+                uint8_t *slot = sm.ring[w][x & (kDbfRing - 1)][sub] + ring_off;
+                *reinterpret_cast<Vec *>(slot) = va;
+                *reinterpret_cast<Vec *>(slot + RB) = vb;
+            }
+        }
+        if (top_glob && t < 4 && !last) *reinterpret_cast<Vec *>(sm.top0[sub] + top_off) = tnext;
+        if (bottom_glob && (x > 0 || last)) {
+            // macroblocks [0, x) (all of them after the last one) are in global memory: publish
+            __threadfence();
             __syncwarp();
-            int c[20];
-#pragma unroll
-            for (int k = 0; k < 20; k++) c[k] = T[k * kLS + i];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int bs = (bh >> (8 * e)) & 0xff;
-                const unsigned need = __ballot_sync(0xffffffffu, bs != 0);
-                if (e == 0) top_edge = need;
-                if (!need) continue;
-                const unsigned strong = __ballot_sync(0xffffffffu, bs == 4);
-                luma_edge_p(c[4 * e], c[4 * e + 1], c[4 * e + 2], c[4 * e + 3], c[4 * e + 4], c[4 * e + 5], c[4 * e + 6],
-                            c[4 * e + 7], bs, e == 0 ? prm.y : prm.z, strong != 0);
-            }
-#pragma unroll
-            for (int k = 1; k < 20; k++) T[k * kLS + i] = (uint8_t)c[k];
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++) r[k] = *reinterpret_cast<const uint32_t *>(T + (i + 4) * kLS + 4 * k);
-            if (i < 4) {
-                top.x = *reinterpret_cast<const uint32_t *>(T + i * kLS + 0);
-                top.y = *reinterpret_cast<const uint32_t *>(T + i * kLS + 4);
-                top.z = *reinterpret_cast<const uint32_t *>(T + i * kLS + 8);
-                top.w = *reinterpret_cast<const uint32_t *>(T + i * kLS + 12);
-            }
-            __syncwarp();
+            if (lane == 0) st_release(prog + row, last ? g.mb_w : x);
         }
-        // rows -3..-1 of the macroblock above: always ours to write when that row handed them over in
-        // shared memory, otherwise only when the top edge changed them
-        if (act && i >= 1 && i < 4 && (rc.top_smem || (rc.top_glob && top_edge)))
-            __stcg(reinterpret_cast<uint4 *>(gtop + 16 * mbx), top);
-        // columns 0..11 are final for this row; 12..15 wait for the next MB's left edge
-        const bool last = mbx == g.mb_w - 1;
-        if (act && mine && (any_v | any_h)) {
-            __stcg(reinterpret_cast<uint2 *>(grow + 16 * mbx), make_uint2(r[0], r[1]));
-            __stcg(reinterpret_cast<uint32_t *>(grow + 16 * mbx + 8), r[2]);
-            if (last) __stcg(reinterpret_cast<uint32_t *>(grow + 16 * mbx + 12), r[3]);
-        }
-        if (rc.bottom_smem) {
-            // the consumer must have finished the macroblock that used this ring slot before
-            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], 2 * (mbx - kDbfRing) + 2, lane);
-            if (i >= 12) {
-                uint32_t *slot = reinterpret_cast<uint32_t *>(&sm.ring[w][mbx % kDbfRing][half][i - 12]);
-                slot[0] = r[0], slot[1] = r[1], slot[2] = r[2];
-                if (last) slot[3] = r[3];
-            }
-        }
-        left = r[3];
-        own = nxt;
+#pragma unroll
+        for (int k = 0; k < NW; k++) cur[0][k] = nxt[0][k], cur[1][k] = nxt[1][k];
         bsw = bsw_n;
         prm = prm_n;
-        dirty_prev = (any_v | any_h) != 0;
-        if (rc.bottom_glob) __threadfence();
-        publish_smem(&sm.progress[w], 2 * mbx + 2, lane);
-        if (rc.bottom_glob && act && i == 0) st_release(prog + row, mbx + 1);
     }
 }
 
-// ---------------------------------------------------------------------------- chroma rows
-// ring slot reuse for chroma: uint4 ring[..][half][plane*2 + (row 6|7)] holds 8 samples in .x/.y
-__device__ __forceinline__ void deblock_chroma_row(DbfSmem &sm, const RowCtx rc, const FrameDesc &fd, const Geometry &g, int half,
-                                                   int i, bool act)
-{
-    const int lane = threadIdx.x & 31, row = rc.row, w = rc.w;
-    const int pl = i >> 3, l = i & 7;          // plane (0 Cb, 1 Cr), line
-    uint8_t *Th = sm.tile[w] + half * kCHalf;
-    uint8_t *T = Th + pl * kCPlane;            // row r at T + (r + 2) * kCS2
-    int *prog = fd.row_progress + 2 * g.mb_h;  // [2]: chroma deblock wavefront (CTA boundaries only)
-    uint8_t *grow = fd.cur[1 + pl] + (ptrdiff_t)(8 * row + l) * g.c_stride;
-    // threads 0..3 of a half also move the two rows above: (plane i>>1, row -2 + (i&1))
-    uint8_t *gtop = fd.cur[1 + ((i >> 1) & 1)] + (ptrdiff_t)(8 * row - 2 + (i & 1)) * g.c_stride;
-    const DeblockSide *side = fd.dbf_bs + (size_t)row * g.mb_w;
-    uint32_t left = 0;
-    uint2 own = make_uint2(0, 0);
-    uint4 prm = make_uint4(0, 0, 0, 0);
-    uint32_t bsw = 0;
-    if (act) {
-        own = __ldcg(reinterpret_cast<const uint2 *>(grow));
-        bsw = __ldg(&side[0].bs[l >> 1]);
-        prm = __ldg(reinterpret_cast<const uint4 *>(side[0].chroma));
-    }
-    const bool poll_g = act && i == 0 && rc.top_glob;
-    const bool mine = !(rc.bottom_smem && l == 7);  // row 7 is finished by the row below inside a CTA
-    const bool to_ring = rc.bottom_smem && l >= 6;
-    bool dirty_prev = false;
-
-    for (int mbx = 0; mbx < g.mb_w; mbx++) {
-        uint2 nxt = make_uint2(0, 0);
-        uint4 prm_n = make_uint4(0, 0, 0, 0);
-        uint32_t bsw_n = 0;
-        if (act && mbx + 1 < g.mb_w) {
-            nxt = __ldcg(reinterpret_cast<const uint2 *>(grow + 8 * (mbx + 1)));
-            bsw_n = __ldg(&side[mbx + 1].bs[l >> 1]);
-            prm_n = __ldg(reinterpret_cast<const uint4 *>(side[mbx + 1].chroma));
-        }
-        // only even luma edges (0 and 2) touch chroma (core/frame.c:597,620)
-        const int bv0 = bsw & 0xf, bv2 = (bsw >> 16) & 0xf, bh0 = (bsw >> 4) & 0xf, bh2 = (bsw >> 20) & 0xf;
-        const unsigned any_v = __ballot_sync(0xffffffffu, (bv0 | bv2) != 0), any_h = __ballot_sync(0xffffffffu, (bh0 | bh2) != 0);
-        int v[12];
-        {
-            const uint32_t wd[3] = {left, own.x, own.y};
-#pragma unroll
-            for (int k = 0; k < 12; k++) v[k] = ub(wd[k >> 2], k & 3);
-        }
-        if (any_v) {
-            chroma_edge_p(v[2], v[3], v[4], v[5], bv0, prm.x);
-            chroma_edge_p(v[6], v[7], v[8], v[9], bv2, prm.z);
-        }
-        if (mbx > 0) {
-            const uint32_t lw = pk4(v[0], v[1], v[2], v[3]);
-            if (act && mine && (dirty_prev || any_v)) __stcg(reinterpret_cast<uint32_t *>(grow + 8 * mbx - 4), lw);
-            if (to_ring) sm.ring[w][(mbx - 1) % kDbfRing][half][pl * 2 + (l - 6)].y = lw;
-        }
-        if (rc.bottom_smem) publish_smem(&sm.progress[w], 2 * mbx + 1, lane);
-        uint32_t r0 = pk4(v[4], v[5], v[6], v[7]), r1 = pk4(v[8], v[9], v[10], v[11]);
-
-        uint2 top = make_uint2(0, 0);
-        if (rc.top_smem) {
-            wait_smem(&sm.progress[w - 1], min(2 * mbx + 3, 2 * g.mb_w), lane);
-            if (i < 4) {
-                const uint4 t4 = sm.ring[w - 1][mbx % kDbfRing][half][i];  // i = plane*2 + (row -2 | -1)
-                top = make_uint2(t4.x, t4.y);
-            }
-        } else {
-            wait_global(prog + row - 1, min(mbx + 2, g.mb_w), poll_g);
-            if (act && rc.top_glob && i < 4 && any_h) top = __ldcg(reinterpret_cast<const uint2 *>(gtop + 8 * mbx));
-        }
-        unsigned top_edge = 0;
-        if (any_h) {
-            *reinterpret_cast<uint32_t *>(T + (l + 2) * kCS2) = r0;
-            *reinterpret_cast<uint32_t *>(T + (l + 2) * kCS2 + 4) = r1;
-            uint8_t *Tt = Th + ((i >> 1) & 1) * kCPlane + (i & 1) * kCS2;
-            if (i < 4) {
-                *reinterpret_cast<uint32_t *>(Tt) = top.x;
-                *reinterpret_cast<uint32_t *>(Tt + 4) = top.y;
-            }
-            __syncwarp();
-            int c[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = T[k * kCS2 + l];  // column l of this plane, rows -2..5
-            chroma_edge_p(c[0], c[1], c[2], c[3], bh0, prm.y);
-            chroma_edge_p(c[4], c[5], c[6], c[7], bh2, prm.z);
-            T[1 * kCS2 + l] = (uint8_t)c[1];
-            T[2 * kCS2 + l] = (uint8_t)c[2];
-            T[5 * kCS2 + l] = (uint8_t)c[5];
-            T[6 * kCS2 + l] = (uint8_t)c[6];
-            __syncwarp();
-            r0 = *reinterpret_cast<const uint32_t *>(T + (l + 2) * kCS2);
-            r1 = *reinterpret_cast<const uint32_t *>(T + (l + 2) * kCS2 + 4);
-            if (i < 4) top = make_uint2(*reinterpret_cast<const uint32_t *>(Tt), *reinterpret_cast<const uint32_t *>(Tt + 4));
-            top_edge = __ballot_sync(0xffffffffu, bh0 != 0);
-            __syncwarp();
-        }
-        // row -1 of the macroblock above (p0 of the top edge), plane (i>>1)
-        if (act && (i & 1) && i < 4 && (rc.top_smem || (rc.top_glob && top_edge)))
-            __stcg(reinterpret_cast<uint2 *>(gtop + 8 * mbx), top);
-        const bool last = mbx == g.mb_w - 1;
-        if (act && mine && (any_v | any_h)) {
-            __stcg(reinterpret_cast<uint32_t *>(grow + 8 * mbx), r0);
-            if (last) __stcg(reinterpret_cast<uint32_t *>(grow + 8 * mbx + 4), r1);
-        }
-        if (rc.bottom_smem) {
-            if (mbx >= kDbfRing) wait_smem(&sm.progress[w + 1], 2 * (mbx - kDbfRing) + 2, lane);
-            if (l >= 6) {
-                uint4 &slot = sm.ring[w][mbx % kDbfRing][half][pl * 2 + (l - 6)];
-                slot.x = r0;
-                if (last) slot.y = r1;
-            }
-        }
-        left = r1;
-        own = nxt;
-        bsw = bsw_n;
-        prm = prm_n;
-        dirty_prev = (any_v | any_h) != 0;
-        if (rc.bottom_glob) __threadfence();
-        publish_smem(&sm.progress[w], 2 * mbx + 2, lane);
-        if (rc.bottom_glob && act && i == 0) st_release(prog + row, mbx + 1);
-    }
-}
-
-// grid: 2 roles x ceil(n_lanes/2) stream pairs x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
-// dependency order (the group above of the same pair and role always has a smaller ticket)
-__global__ void __launch_bounds__(32 * kDbfRows, 4) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes,
-                                                                   int *ticket, int dbg)
+// grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
+// dependency order (the group above of the same quad and role always has a smaller ticket)
+__global__ void __launch_bounds__(32 * kDbfRows, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket)
 {
     __shared__ __align__(16) DbfSmem sm;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) sm.ticket = atomicAdd(ticket, 1);
-    if (threadIdx.x < kDbfRows) sm.progress[threadIdx.x] = 0;
     __syncthreads();
-    const int t = sm.ticket;
+    const int tk = sm.ticket;
     const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
-    const int role = t & 1, u = t >> 1;
-    const int pair = u / groups, grp = u % groups;
-    RowCtx rc;
-    rc.w = w;
-    rc.row = grp * kDbfRows + w;
-    if (rc.row >= g.mb_h) return;
-    rc.top_smem = w > 0;
-    rc.top_glob = w == 0 && rc.row > 0;
-    rc.bottom_smem = w + 1 < kDbfRows && rc.row + 1 < g.mb_h;
-    rc.bottom_glob = !rc.bottom_smem && rc.row + 1 < g.mb_h;
-    const int half = lane >> 4, i = lane & 15;
-    const int stream = 2 * pair + half;
-    const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
-    const bool act = stream < n_lanes && fd.deblock != 0;
-    (void)dbg;
+    const int role = tk & 1, u = tk >> 1;
+    const int quad = u / groups, grp = u % groups;
     if (role == 0)
-        deblock_luma_row(sm, rc, fd, g, half, i, act);
+        deblock_rows<false>(sm, descs, g, n_lanes, quad, grp);
     else
-        deblock_chroma_row(sm, rc, fd, g, half, i, act);
+        deblock_rows<true>(sm, descs, g, n_lanes, quad, grp);
 }
 #endif  // P264B200_DEFINE_KERNELS
 

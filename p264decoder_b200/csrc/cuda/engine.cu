@@ -436,8 +436,8 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
     const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
                       2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
     for (int gi = 0; gi < G; gi++) {
-        // lanes [l0, l1) of this group; pairs of lanes share a deblock warp, so groups start on even lanes
-        const int per = ((n_lanes + G - 1) / G + 1) & ~1;
+        // lanes [l0, l1) of this group; four lanes share a deblock warp, so groups start on multiples of four
+        const int per = ((n_lanes + G - 1) / G + kDbfQuad - 1) & ~(kDbfQuad - 1);
         const int l0 = gi * per, l1 = l0 + per < n_lanes ? l0 + per : n_lanes;
         if (l0 >= l1) break;
         const int nl = l1 - l0;
@@ -472,7 +472,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + 1) / 2) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfRows, 0, st>>>(descs, g, nl, tickets + 1, e->dbg);
+            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfRows, 0, st>>>(descs, g, nl, tickets + 1);
         }
         {
             ProfScope p(e, K_BORDER, st);
