@@ -170,7 +170,7 @@ constexpr int kDbfSlot = 80;    // bytes per (slot, stream): 4 rows x 16 B, + 16
 struct DbfSmem {
     uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];              // luma: row r at 16r; chroma: plane p row r at 64p + 8r
     uint8_t ring[kDbfRows][kDbfRing][kDbfQuad][kDbfSlot];    // luma: rows 12..15 at 16k; chroma: plane p rows 6,7 at 16p + 8k
-    uint8_t top0[kDbfQuad][kDbfSlot];                         // same layout: rows above warp 0, fetched from global memory
+    uint8_t topring[kDbfRing][kDbfQuad][kDbfSlot];            // same layout: rows above warp 0, fetched from global memory by the I/O warp
     int ticket;
 };
 
@@ -232,13 +232,11 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     const int row = grp * kDbfRows + w;
     const bool row_ok = row < g.mb_h;
     const bool has_top = row > 0;
-    const bool top_smem = w > 0, top_glob = w == 0 && has_top;
+    const bool top_smem = w > 0;
     const bool bottom_smem = w + 1 < kDbfRows && row + 1 < g.mb_h;
-    const bool bottom_glob = !bottom_smem && row + 1 < g.mb_h;
     const int stream = kDbfQuad * quad + sub;
     const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
     const bool act = row_ok && stream < n_lanes && fd.deblock != 0;
-    int *prog = descs[kDbfQuad * quad].row_progress + (C ? 2 : 1) * g.mb_h;  // one progress word per (quad, role, row)
     const int stride = C ? g.c_stride : g.y_stride;
     // this thread's two sample rows, and (threads 0..3) the row above it moves between global and shared memory:
     // luma row -4 + t; chroma plane t >> 1, row -2 + (t & 1)
@@ -255,20 +253,14 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     uint32_t prev[2][NW], cur[2][NW], nxt[2][NW];
     uint32_t bsw = 0, bsw_n = 0;
     uint4 prm = make_uint4(0, 0, 0, 0), prm_n = prm;
-    Vec tnext;
 #pragma unroll
     for (int k = 0; k < NW; k++) prev[0][k] = prev[1][k] = cur[0][k] = cur[1][k] = nxt[0][k] = nxt[1][k] = 0;
-    {
-        uint32_t z[4] = {0, 0, 0, 0};
-        vec_set(tnext, z);
-    }
     if (act) {
         vec_get(__ldcg(reinterpret_cast<const Vec *>(grow)), cur[0]);
         vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + stride)), cur[1]);
         bsw = __ldg(&side[0].bs[j >> (C ? 0 : 1)]);
         prm = __ldg(reinterpret_cast<const uint4 *>(C ? side[0].chroma : side[0].luma));
     }
-    int seen = 0;  // newest progress value of the row above (global hand-off only)
 
     const int n_steps = g.mb_w + 2 * (kDbfRows - 1);
 #pragma unroll 1
@@ -278,23 +270,12 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         if (x < 0 || x >= g.mb_w || !row_ok) continue;
         const bool last = x == g.mb_w - 1;
 
-        // ---- rows above through global memory: one thread polls, one macroblock ahead of need, so that the
-        // fetch of the next macroblock's rows overlaps this macroblock's filtering
-        if (top_glob) {
-            const int need = min(x + 2, g.mb_w);
-            if (seen < need) {
-                if (lane == 0) {
-                    int spins = 0;
-                    while ((seen = ld_acquire(prog + row - 1)) < need) __nanosleep(++spins < 16 ? 40 : 400);
-                }
-                seen = __shfl_sync(0xffffffffu, seen, 0);
-            }
-            if (x == 0) {
-                if (act && t < 4) *reinterpret_cast<Vec *>(sm.top0[sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop));
-            }
-            if (act && t < 4 && !last) tnext = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (x + 1)));
+        // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull the
+        // next line into L2 so that those loads do not wait on HBM inside the dependent chain)
+        if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + RB * x + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + stride + RB * x + 128));
         }
-        // ---- prefetch the next macroblock's rows, strengths and parameters
         if (act && !last) {
             vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + RB * (x + 1))), nxt[0]);
             vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + stride + RB * (x + 1))), nxt[1]);
@@ -352,7 +333,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
             *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
             *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
         }
-        uint8_t *slot_top = (top_smem ? sm.ring[w - 1][x & (kDbfRing - 1)][sub] : sm.top0[sub]);
+        uint8_t *slot_top = top_smem ? sm.ring[w - 1][x & (kDbfRing - 1)][sub] : sm.topring[x & (kDbfRing - 1)][sub];
         uint8_t *topp = slot_top + (C ? 16 * pl : 0);
         __syncwarp();
         {
@@ -398,13 +379,6 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
                 *reinterpret_cast<Vec *>(slot + RB) = vb;
             }
         }
-        if (top_glob && t < 4 && !last) *reinterpret_cast<Vec *>(sm.top0[sub] + top_off) = tnext;
-        if (bottom_glob && (x > 0 || last)) {
-            // macroblocks [0, x) (all of them after the last one) are in global memory: publish
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release(prog + row, last ? g.mb_w : x);
-        }
 #pragma unroll
         for (int k = 0; k < NW; k++) cur[0][k] = nxt[0][k], cur[1][k] = nxt[1][k];
         bsw = bsw_n;
@@ -412,9 +386,79 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     }
 }
 
+// The I/O warp of a CTA (warp kDbfRows): everything that touches the global progress words, so that no
+// filtering warp ever executes a fence or polls.  Per lockstep step s it
+//  * (consumer side, row group > 0) keeps the rows above warp 0 two macroblocks ahead in sm.topring: waits for
+//    the row group above to have stored macroblock s+2, loads its last rows, and drops them into the ring one
+//    step later (warp 0 reads slot s at step s);
+//  * (producer side) publishes how many macroblocks of the CTA's last row are in global memory.  The barrier
+//    orders that row's stores before this warp's fence + release (fence cumulativity), one step behind.
+template <bool C>
+__device__ __forceinline__ void deblock_io_warp(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
+                                                int grp)
+{
+    constexpr int RB = C ? 8 : 16, NR = C ? 8 : 16;
+    typedef typename DbfVec<RB / 4>::type Vec;
+    const int lane = threadIdx.x & 31, sub = (lane >> 2) & 3, k = lane & 3;  // lanes 0..15: (stream, row above)
+    const int row0 = grp * kDbfRows;                 // first macroblock row of the CTA
+    const int last_w = kDbfRows - 1, row_last = row0 + last_w;
+    const bool consumer = grp > 0, producer = row_last + 1 < g.mb_h;
+    const int stream = kDbfQuad * quad + sub;
+    const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
+    const bool act = lane < 16 && stream < n_lanes && fd.deblock != 0;
+    int *prog = descs[kDbfQuad * quad].row_progress + (C ? 2 : 1) * g.mb_h;  // one progress word per (quad, role, row)
+    const int stride = C ? g.c_stride : g.y_stride;
+    // luma: row -4 + k; chroma: plane k >> 1, row -2 + (k & 1)
+    const uint8_t *gtop = C ? fd.cur[1 + (k >> 1)] + (ptrdiff_t)(NR * row0 - 2 + (k & 1)) * stride : fd.cur[0] + (ptrdiff_t)(NR * row0 - 4 + k) * stride;
+    const int top_off = C ? 16 * (k >> 1) + 8 * (k & 1) : 16 * k;
+    int seen = 0;
+    auto wait_for = [&](int need) {
+        if (seen < need) {
+            if (lane == 0) {
+                int spins = 0;
+                while ((seen = ld_acquire(prog + row0 - 1)) < need) __nanosleep(++spins < 16 ? 40 : 400);
+            }
+            seen = __shfl_sync(0xffffffffu, seen, 0);
+        }
+    };
+    Vec pend;
+    {
+        uint32_t z[4] = {0, 0, 0, 0};
+        vec_set(pend, z);
+    }
+    if (consumer) {
+        // macroblocks 0 and 1 before the first step
+        wait_for(min(2, g.mb_w));
+        if (act) {
+            *reinterpret_cast<Vec *>(sm.topring[0][sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop));
+            if (g.mb_w > 1) *reinterpret_cast<Vec *>(sm.topring[1][sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop + RB));
+        }
+    }
+    const int n_steps = g.mb_w + 2 * (kDbfRows - 1);
+#pragma unroll 1
+    for (int s = 0; s <= n_steps; s++) {
+        __syncthreads();  // s == n_steps: the extra barrier after the loop of the filtering warps
+        if (consumer && s < n_steps) {
+            if (s >= 1 && s + 1 < g.mb_w && act) *reinterpret_cast<Vec *>(sm.topring[(s + 1) & (kDbfRing - 1)][sub] + top_off) = pend;
+            if (s + 2 < g.mb_w) {
+                wait_for(min(s + 3, g.mb_w));
+                if (act) pend = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (s + 2)));
+            }
+        }
+        if (producer) {
+            // the last row worked on macroblock x7 during step s-1: macroblocks [0, x7) are stored, all after the last
+            const int x7 = s - 1 - 2 * last_w;
+            if (x7 >= 1 && x7 < g.mb_w && lane == 0) {
+                __threadfence();
+                st_release(prog + row_last, x7 == g.mb_w - 1 ? g.mb_w : x7);
+            }
+        }
+    }
+}
+
 // grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
 // dependency order (the group above of the same quad and role always has a smaller ticket)
-__global__ void __launch_bounds__(32 * kDbfRows, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket)
+__global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket)
 {
     __shared__ __align__(16) DbfSmem sm;
     if (threadIdx.x == 0) sm.ticket = atomicAdd(ticket, 1);
@@ -423,10 +467,18 @@ __global__ void __launch_bounds__(32 * kDbfRows, 2) deblock_kernel(const FrameDe
     const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
     const int role = tk & 1, u = tk >> 1;
     const int quad = u / groups, grp = u % groups;
+    if (threadIdx.x >= 32 * kDbfRows) {
+        if (role == 0)
+            deblock_io_warp<false>(sm, descs, g, n_lanes, quad, grp);
+        else
+            deblock_io_warp<true>(sm, descs, g, n_lanes, quad, grp);
+        return;
+    }
     if (role == 0)
         deblock_rows<false>(sm, descs, g, n_lanes, quad, grp);
     else
         deblock_rows<true>(sm, descs, g, n_lanes, quad, grp);
+    __syncthreads();  // lets the I/O warp publish the last row's final macroblock
 }
 #endif  // P264B200_DEFINE_KERNELS
 
