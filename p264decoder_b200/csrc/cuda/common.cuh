@@ -192,6 +192,35 @@ __device__ __forceinline__ void residual4x4(const int16_t *__restrict__ lvl, int
     idct4x4_add(d, px);
 }
 
+// prefetch loads that must be ISSUED where they are written (the compiler is free to sink an ordinary
+// read-only load down to its first use, which puts the whole memory latency back into the dependent chain)
+__device__ __forceinline__ uint4 ldg_now_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_now_v2(const void *p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void ldg_now(const void *p, uint4 &v) { v = ldg_now_v4(p); }
+__device__ __forceinline__ void ldg_now(const void *p, uint2 &v) { v = ldg_now_v2(p); }
+__device__ __forceinline__ uint32_t ldg_now_u32(const void *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // wavefront flag helpers (global memory, visible across SMs)
 __device__ __forceinline__ int ld_acquire(const int *p)
 {

@@ -15,11 +15,12 @@
 //  * a warp owns one macroblock row of FOUR lanes (streams): 8 threads per stream, always in the
 //    same code path.  Luma and chroma are independent given the boundary strengths and run as
 //    separate warps (role = CTA) with separate progress flags;
-//  * a CTA owns kDbfRows consecutive macroblock rows and runs them in LOCKSTEP: one __syncthreads per
-//    macroblock step, warp w works on macroblock (step - 2w).  Waiting warps sit in the barrier
-//    instead of polling.  The four sample rows that cross a row boundary are handed down through a
+//  * a CTA owns kDbfRows consecutive macroblock rows and runs them in LOCKSTEP: two __syncthreads per
+//    macroblock step (vertical edges | horizontal edges), warp w works on macroblock (step - w): a
+//    ONE-macroblock lag between rows.  Waiting warps sit in the barrier instead of polling.  The four sample rows that cross a row boundary are handed down through a
 //    small shared-memory ring; only every kDbfRows-th row boundary goes through global memory
-//    (progress word + acquire/release), polled by one thread, one macroblock ahead of need;
+//    (progress word + acquire/release), handled by a ninth "I/O" warp so that no filtering warp ever
+//    executes a fence or polls;
 //  * vertical edges are filtered in registers straight from two 16-byte row loads; the transpose for
 //    the horizontal edges is a shared-memory tile written as rows and read as 16-bit column pairs;
 //  * all global traffic is full 16-byte (luma) / 8-byte (chroma) rows: a macroblock's rows are stored
@@ -167,6 +168,22 @@ constexpr int kDbfRing = 4;     // hand-off slots per producer row (the consumer
 constexpr int kDbfTile = 272;   // bytes per (warp, stream) transpose tile: 16 rows x 16 B, + 16 B bank skew
 constexpr int kDbfSlot = 80;    // bytes per (slot, stream): 4 rows x 16 B, + 16 B bank skew
 
+// Optional per-step cycle trace of ONE CTA (engine debug knob P264B200_TRACE=<ticket>): [warp][step][marks]:
+// 0 after the first barrier of a step, 1 before the second, 2 after it, 3 at the end of the step
+constexpr int kDbfTraceSteps = 320;
+__device__ long long g_dbf_trace[kDbfRows + 1][kDbfTraceSteps][6];
+__device__ long long g_dbf_cta_ns[2048][4];  // per ticket: %globaltimer at kernel entry, first step, last step, exit
+__device__ __forceinline__ long long dbf_now_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void dbf_mark(bool on, int w, int s, int k)
+{
+    if (on && s < kDbfTraceSteps && (threadIdx.x & 31) == 0) g_dbf_trace[w][s][k] = clock64();
+}
+
 struct DbfSmem {
     uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];              // luma: row r at 16r; chroma: plane p row r at 64p + 8r
     uint8_t ring[kDbfRows][kDbfRing][kDbfQuad][kDbfSlot];    // luma: rows 12..15 at 16k; chroma: plane p rows 6,7 at 16p + 8k
@@ -174,31 +191,66 @@ struct DbfSmem {
     int ticket;
 };
 
-// one luma edge on two lines: v -> p3 p2 p1 p0 q0 q1 q2 q3
-__device__ __forceinline__ void dbf_luma_edge2(uint32_t *v, int bs, uint32_t prm, bool mb_edge)
+// Edge parameters of one direction of one macroblock, resolved once per thread: the macroblock edge (left or
+// top) and the three inner edges share alpha / beta per kind; only tc0 and the on/off switch follow bS.
+struct DbfDir {
+    uint32_t prm_mb, prm_in;       // packed parameters (see DeblockSide) of the macroblock edge / the inner edges
+    uint32_t na_mb, nb_mb;         // -alpha, -beta in both fields
+    uint32_t na_in, nb_in;
+};
+__device__ __forceinline__ DbfDir dbf_dir(uint32_t prm_mb, uint32_t prm_in)
 {
-    if (!__any_sync(0xffffffffu, bs != 0)) return;
-    const int alpha = prm & 0xff, beta = (prm >> 8) & 31, tc0 = (prm >> (8 + 5 * bs)) & 31;
-    const swar::EdgeK k = swar::edge_k((unsigned)(bs - 1) < 3u ? alpha : 0, beta, tc0);
-    swar::luma_normal(v[1], v[2], v[3], v[4], v[5], v[6], k);
-    if (mb_edge && __any_sync(0xffffffffu, bs == 4)) {
-        // intra macroblock edge: the strong filter replaces the (disabled) normal one on those lines
-        const swar::EdgeK k4 = swar::edge_k(bs == 4 ? alpha : 0, beta, 0);
+    DbfDir d;
+    d.prm_mb = prm_mb, d.prm_in = prm_in;
+    d.na_mb = swar::rep2(-(int)(prm_mb & 0xff)), d.nb_mb = swar::rep2(-(int)((prm_mb >> 8) & 31));
+    d.na_in = swar::rep2(-(int)(prm_in & 0xff)), d.nb_in = swar::rep2(-(int)((prm_in >> 8) & 31));
+    return d;
+}
+// constants of edge e for boundary strength bs: filtering is switched off by alpha = 0 (bS 0; for luma also bS 4,
+// which the strong filter handles)
+__device__ __forceinline__ swar::EdgeK dbf_edge_k(const DbfDir &d, bool mb_edge, int bs, bool luma)
+{
+    const uint32_t prm = mb_edge ? d.prm_mb : d.prm_in;
+    swar::EdgeK k;
+    const bool on = luma ? (unsigned)(bs - 1) < 3u : bs != 0;
+    k.n_alpha = on ? (mb_edge ? d.na_mb : d.na_in) : 0u;
+    k.n_beta = mb_edge ? d.nb_mb : d.nb_in;
+    k.tc0 = ((prm >> (8 + 5 * bs)) & 31) * swar::kOnes;
+    return k;
+}
+
+// The four luma edges of one direction on two lines, v = 4 samples before the macroblock + its 16 samples.
+// bs4: bS of edge e in bits 8e..8e+3.  The bS < 4 filters are straight-line code with no votes or branches
+// between the edges, so the instruction scheduler can overlap them (edge e+1 needs edge e only through one tap).
+__device__ __forceinline__ void dbf_luma_dir(uint32_t *v, uint32_t bs4, const DbfDir &d)
+{
+    if (!__any_sync(0xffffffffu, bs4 != 0)) return;
+    const int bs0 = bs4 & 0xf;
+    if (__any_sync(0xffffffffu, bs0 == 4)) {
+        // intra macroblock edge: the strong filter, only on the lines that have bS 4 (the normal one is off there)
+        const int alpha = d.prm_mb & 0xff;
+        swar::EdgeK k4;
+        k4.n_alpha = bs0 == 4 ? d.na_mb : 0u, k4.n_beta = d.nb_mb, k4.tc0 = 0;
         swar::luma_strong(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], k4, alpha);
     }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const swar::EdgeK k = dbf_edge_k(d, e == 0, (bs4 >> (8 * e)) & 0xf, true);
+        swar::luma_normal(v[4 * e + 1], v[4 * e + 2], v[4 * e + 3], v[4 * e + 4], v[4 * e + 5], v[4 * e + 6], k);
+    }
 }
-// one chroma edge on two lines: v -> p1 p0 q0 q1
-__device__ __forceinline__ void dbf_chroma_edge2(uint32_t *v, int bs, uint32_t prm, bool mb_edge)
+// The two chroma edges of one direction on two lines, v = p1 p0 | q0 q1 . . q0' q1' ...: edge 0 at v[2], edge 2 at v[6]
+__device__ __forceinline__ void dbf_chroma_dir(uint32_t *v, int bs0, int bs2, const DbfDir &d)
 {
-    if (!__any_sync(0xffffffffu, bs != 0)) return;
-    const int alpha = prm & 0xff, beta = (prm >> 8) & 31, tc0 = (prm >> (8 + 5 * bs)) & 31;
-    const swar::EdgeK k = swar::edge_k(bs != 0 ? alpha : 0, beta, tc0);
+    if (!__any_sync(0xffffffffu, (bs0 | bs2) != 0)) return;
+    const swar::EdgeK k0 = dbf_edge_k(d, true, bs0, false), k2 = dbf_edge_k(d, false, bs2, false);
     uint32_t p0 = v[1], q0 = v[2];
-    swar::chroma_edge2(v[0], p0, q0, v[3], k, false);
-    if (mb_edge && __any_sync(0xffffffffu, bs == 4)) {
+    swar::chroma_edge2(v[0], p0, q0, v[3], k0, false);
+    swar::chroma_edge2(v[4], v[5], v[6], v[7], k2, false);
+    if (__any_sync(0xffffffffu, bs0 == 4)) {
         uint32_t sp0 = v[1], sq0 = v[2];
-        swar::chroma_edge2(v[0], sp0, sq0, v[3], k, true);
-        if (bs == 4) p0 = sp0, q0 = sq0;
+        swar::chroma_edge2(v[0], sp0, sq0, v[3], k0, true);
+        if (bs0 == 4) p0 = sp0, q0 = sq0;
     }
     v[1] = p0, v[2] = q0;
 }
@@ -216,7 +268,7 @@ __device__ __forceinline__ void vec_set(uint2 &v, const uint32_t *r) { v = make_
 // threads 0..3 of a stream on Cb, 4..7 on Cr).
 template <bool C>
 __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
-                                             int grp)
+                                             int grp, bool trace, bool times_on, int tk)
 {
     constexpr int NW = C ? 2 : 4;    // 32-bit words per sample row of a macroblock
     constexpr int RB = 4 * NW;       // bytes per row
@@ -262,80 +314,97 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         prm = __ldg(reinterpret_cast<const uint4 *>(C ? side[0].chroma : side[0].luma));
     }
 
-    const int n_steps = g.mb_w + 2 * (kDbfRows - 1);
+    // Lockstep schedule, one-macroblock lag: step s = [barrier] vertical edges of MB (s - w) [barrier] horizontal
+    // edges of MB (s - w).  The left-edge filter of MB x+1 finalises the last columns of MB x in the first half of
+    // a step, so the row below can filter the top edge of its MB x in the second half of the same step.
+    const int n_steps = g.mb_w + (kDbfRows - 1);
 #pragma unroll 1
     for (int s = 0; s < n_steps; s++) {
-        __syncthreads();
-        const int x = s - 2 * w;
-        if (x < 0 || x >= g.mb_w || !row_ok) continue;
+        const int x = s - w;
+        const bool on = x >= 0 && x < g.mb_w && row_ok;
         const bool last = x == g.mb_w - 1;
-
-        // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull the
-        // next line into L2 so that those loads do not wait on HBM inside the dependent chain)
-        if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + RB * x + 128));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + stride + RB * x + 128));
-        }
-        if (act && !last) {
-            vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + RB * (x + 1))), nxt[0]);
-            vec_get(__ldcg(reinterpret_cast<const Vec *>(grow + stride + RB * (x + 1))), nxt[1]);
-            bsw_n = __ldg(&side[x + 1].bs[j >> (C ? 0 : 1)]);
-            prm_n = __ldg(reinterpret_cast<const uint4 *>(C ? side[x + 1].chroma : side[x + 1].luma));
-        }
-
-        // ---- vertical edges: taps of this thread's two rows, two rows per register
-        {
-            uint32_t P[NP];
-#pragma unroll
-            for (int wd = 0; wd < 1 + NW; wd++) {
-                const uint32_t wa = wd == 0 ? prev[0][NW - 1] : cur[0][wd - 1], wb = wd == 0 ? prev[1][NW - 1] : cur[1][wd - 1];
-                const uint32_t t01 = prmt(wa, wb, 0x5140), t23 = prmt(wa, wb, 0x7362);
-                P[4 * wd + 0] = prmt(t01, 0, 0x4140);
-                P[4 * wd + 1] = prmt(t01, 0, 0x4342);
-                P[4 * wd + 2] = prmt(t23, 0, 0x4140);
-                P[4 * wd + 3] = prmt(t23, 0, 0x4342);
+        dbf_mark(trace, w, s, 3);
+        __syncthreads();
+        dbf_mark(trace, w, s, 0);
+        if (times_on && threadIdx.x == 0 && (s == 0 || s == n_steps - 1)) g_dbf_cta_ns[tk][s == 0 ? 1 : 2] = dbf_now_ns();
+        if (on) {
+            // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull
+            // the next line into L2 so that those loads do not wait on HBM inside the dependent chain)
+            if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + RB * x + 128));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + stride + RB * x + 128));
             }
-            if (C) {
-                dbf_chroma_edge2(P + 2, bsw & 0xf, prm.x, true);
-                dbf_chroma_edge2(P + 6, (bsw >> 16) & 0xf, prm.z, false);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++) dbf_luma_edge2(P + 4 * e, (bsw >> (8 * e)) & 0xf, e == 0 ? prm.x : prm.z, e == 0);
+            if (act && !last) {
+                bsw_n = ldg_now_u32(&side[x + 1].bs[j >> (C ? 0 : 1)]);
+                {
+                    // (two loads with no unused component: the register of an unused one would be recycled as scratch
+                    // while the prefetch is still in flight, and that write has to wait out the whole memory latency)
+                    const uint32_t *pp = C ? side[x + 1].chroma : side[x + 1].luma;
+                    const uint2 xy = ldg_now_v2(pp);
+                    prm_n.x = xy.x, prm_n.y = xy.y, prm_n.z = ldg_now_u32(pp + 2);
+                }
+                // (this row's samples were written by the previous kernel; nobody else touches them before we do)
+                Vec va, vb;
+                ldg_now(grow + RB * (x + 1), va);
+                ldg_now(grow + stride + RB * (x + 1), vb);
+                vec_get(va, nxt[0]);
+                vec_get(vb, nxt[1]);
             }
+            // ---- vertical edges: taps of this thread's two rows, two rows per register
+            {
+                uint32_t P[NP];
 #pragma unroll
-            for (int wd = 0; wd < 1 + NW; wd++) {
-                const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
-                const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
-                if (wd == 0)
-                    prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
+                for (int wd = 0; wd < 1 + NW; wd++) {
+                    const uint32_t wa = wd == 0 ? prev[0][NW - 1] : cur[0][wd - 1], wb = wd == 0 ? prev[1][NW - 1] : cur[1][wd - 1];
+                    const uint32_t t01 = prmt(wa, wb, 0x5140), t23 = prmt(wa, wb, 0x7362);
+                    P[4 * wd + 0] = prmt(t01, 0, 0x4140);
+                    P[4 * wd + 1] = prmt(t01, 0, 0x4342);
+                    P[4 * wd + 2] = prmt(t23, 0, 0x4140);
+                    P[4 * wd + 3] = prmt(t23, 0, 0x4342);
+                }
+                const DbfDir dv = dbf_dir(prm.x, prm.z);
+                if (C)
+                    dbf_chroma_dir(P + 2, bsw & 0xf, (bsw >> 16) & 0xf, dv);
                 else
-                    cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
+                    dbf_luma_dir(P, bsw & 0x0f0f0f0fu, dv);
+#pragma unroll
+                for (int wd = 0; wd < 1 + NW; wd++) {
+                    const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
+                    const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
+                    if (wd == 0)
+                        prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
+                    else
+                        cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
+                }
+            }
+            // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
+            if (x > 0) {
+                Vec va, vb;
+                vec_set(va, prev[0]);
+                vec_set(vb, prev[1]);
+                if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * (x - 1)) = va;
+                if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * (x - 1)) = vb;
+                if (to_ring) {
+                    uint8_t *slot = sm.ring[w][(x - 1) & (kDbfRing - 1)][sub] + ring_off;
+                    *reinterpret_cast<Vec *>(slot) = va;
+                    *reinterpret_cast<Vec *>(slot + RB) = vb;
+                }
+            }
+            // ---- transpose through shared memory: rows in, 16-bit column pairs out
+            {
+                Vec va, vb;
+                vec_set(va, cur[0]);
+                vec_set(vb, cur[1]);
+                *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
+                *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
             }
         }
-        // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
-        if (x > 0) {
-            Vec va, vb;
-            vec_set(va, prev[0]);
-            vec_set(vb, prev[1]);
-            if (act && store_a) __stcg(reinterpret_cast<Vec *>(grow + RB * (x - 1)), va);
-            if (act && store_b) __stcg(reinterpret_cast<Vec *>(grow + stride + RB * (x - 1)), vb);
-            if (to_ring) {
-                uint8_t *slot = sm.ring[w][(x - 1) & (kDbfRing - 1)][sub] + ring_off;
-                *reinterpret_cast<Vec *>(slot) = va;
-                *reinterpret_cast<Vec *>(slot + RB) = vb;
-            }
-        }
-        // ---- transpose through shared memory: rows in, 16-bit column pairs out
-        {
-            Vec va, vb;
-            vec_set(va, cur[0]);
-            vec_set(vb, cur[1]);
-            *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
-            *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
-        }
+        dbf_mark(trace, w, s, 1);
+        __syncthreads();
+        dbf_mark(trace, w, s, 2);
+        if (!on) continue;
         uint8_t *slot_top = top_smem ? sm.ring[w - 1][x & (kDbfRing - 1)][sub] : sm.topring[x & (kDbfRing - 1)][sub];
         uint8_t *topp = slot_top + (C ? 16 * pl : 0);
-        __syncwarp();
         {
             uint32_t Q[NQ];
 #pragma unroll
@@ -343,16 +412,15 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
                 const uint8_t *src = k < TR ? topp + RB * k + 2 * j : T + RB * (k - TR) + 2 * j;
                 Q[k] = (k < TR && !has_top) ? 0u : prmt(*reinterpret_cast<const uint16_t *>(src), 0, 0x4140);
             }
+            const DbfDir dh = dbf_dir(prm.y, prm.z);
             if (C) {
-                dbf_chroma_edge2(Q + 0, (bsw >> 4) & 0xf, prm.y, true);
-                dbf_chroma_edge2(Q + 4, (bsw >> 20) & 0xf, prm.z, false);
+                dbf_chroma_dir(Q, (bsw >> 4) & 0xf, (bsw >> 20) & 0xf, dh);
                 if (has_top) *reinterpret_cast<uint16_t *>(topp + RB * 1 + 2 * j) = (uint16_t)prmt(Q[1], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 0 + 2 * j) = (uint16_t)prmt(Q[2], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 3 + 2 * j) = (uint16_t)prmt(Q[5], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 4 + 2 * j) = (uint16_t)prmt(Q[6], 0, 0x4420);
             } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++) dbf_luma_edge2(Q + 4 * e, (bsw >> (8 * e + 4)) & 0xf, e == 0 ? prm.y : prm.z, e == 0);
+                dbf_luma_dir(Q, (bsw >> 4) & 0x0f0f0f0fu, dh);
 #pragma unroll
                 for (int k = 1; k < NQ - 1; k++) {
                     uint8_t *dst = k < TR ? topp + RB * k + 2 * j : T + RB * (k - TR) + 2 * j;
@@ -366,13 +434,13 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         vec_get(*reinterpret_cast<const Vec *>(T + RB * (2 * j + 1)), prev[1]);
         // the rows above are finished: luma rows -3..-1, chroma row -1 (rows -4 / -2 are only read)
         if (has_top && act && t < 4 && (C ? (t & 1) : (t != 0)))
-            __stcg(reinterpret_cast<Vec *>(gtop + RB * x), *reinterpret_cast<const Vec *>(slot_top + top_off));
+            *reinterpret_cast<Vec *>(gtop + RB * x) = *reinterpret_cast<const Vec *>(slot_top + top_off);
         if (last) {
             Vec va, vb;
             vec_set(va, prev[0]);
             vec_set(vb, prev[1]);
-            if (act && store_a) __stcg(reinterpret_cast<Vec *>(grow + RB * x), va);
-            if (act && store_b) __stcg(reinterpret_cast<Vec *>(grow + stride + RB * x), vb);
+            if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * x) = va;
+            if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * x) = vb;
             if (to_ring) {
                 uint8_t *slot = sm.ring[w][x & (kDbfRing - 1)][sub] + ring_off;
                 *reinterpret_cast<Vec *>(slot) = va;
@@ -395,7 +463,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
 //    orders that row's stores before this warp's fence + release (fence cumulativity), one step behind.
 template <bool C>
 __device__ __forceinline__ void deblock_io_warp(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
-                                                int grp)
+                                                int grp, bool trace)
 {
     constexpr int RB = C ? 8 : 16, NR = C ? 8 : 16;
     typedef typename DbfVec<RB / 4>::type Vec;
@@ -434,31 +502,41 @@ __device__ __forceinline__ void deblock_io_warp(DbfSmem &sm, const FrameDesc *__
             if (g.mb_w > 1) *reinterpret_cast<Vec *>(sm.topring[1][sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop + RB));
         }
     }
-    const int n_steps = g.mb_w + 2 * (kDbfRows - 1);
+    const int n_steps = g.mb_w + (kDbfRows - 1);
+    int peek = 0;  // progress word read asynchronously during the previous step
 #pragma unroll 1
     for (int s = 0; s <= n_steps; s++) {
+        dbf_mark(trace, kDbfRows, s, 3);
         __syncthreads();  // s == n_steps: the extra barrier after the loop of the filtering warps
-        if (consumer && s < n_steps) {
-            if (s >= 1 && s + 1 < g.mb_w && act) *reinterpret_cast<Vec *>(sm.topring[(s + 1) & (kDbfRing - 1)][sub] + top_off) = pend;
-            if (s + 2 < g.mb_w) {
-                wait_for(min(s + 3, g.mb_w));
-                if (act) pend = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (s + 2)));
-            }
-        }
+        dbf_mark(trace, kDbfRows, s, 0);
+        if (consumer && s >= 1 && s + 1 < g.mb_w && act) *reinterpret_cast<Vec *>(sm.topring[(s + 1) & (kDbfRing - 1)][sub] + top_off) = pend;
         if (producer) {
-            // the last row worked on macroblock x7 during step s-1: macroblocks [0, x7) are stored, all after the last
-            const int x7 = s - 1 - 2 * last_w;
+            // the last row worked on macroblock x7 during step s-1: macroblocks [0, x7) are stored, all after the last.
+            // (before this step's loads are issued, so that the fence does not wait for them)
+            const int x7 = s - 1 - last_w;
             if (x7 >= 1 && x7 < g.mb_w && lane == 0) {
                 __threadfence();
                 st_release(prog + row_last, x7 == g.mb_w - 1 ? g.mb_w : x7);
             }
+        }
+        if (consumer && s + 2 < g.mb_w) {
+            seen = max(seen, __shfl_sync(0xffffffffu, peek, 0));
+            wait_for(min(s + 3, g.mb_w));  // normally satisfied by the value peeked one step ago
+            __threadfence();               // acquire side for the peeked (relaxed) value
+            if (act) pend = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (s + 2)));
+            if (lane == 0) peek = ld_relaxed(prog + row0 - 1);
+        }
+        if (s < n_steps) {
+            dbf_mark(trace, kDbfRows, s, 1);
+            __syncthreads();
+            dbf_mark(trace, kDbfRows, s, 2);
         }
     }
 }
 
 // grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
 // dependency order (the group above of the same quad and role always has a smaller ticket)
-__global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket)
+__global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int trace_ticket)
 {
     __shared__ __align__(16) DbfSmem sm;
     if (threadIdx.x == 0) sm.ticket = atomicAdd(ticket, 1);
@@ -467,17 +545,21 @@ __global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const F
     const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
     const int role = tk & 1, u = tk >> 1;
     const int quad = u / groups, grp = u % groups;
+    const bool trace = tk == trace_ticket;
+    const bool times = trace_ticket >= 0 && tk < 2048 && threadIdx.x == 0;
+    if (times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
     if (threadIdx.x >= 32 * kDbfRows) {
         if (role == 0)
-            deblock_io_warp<false>(sm, descs, g, n_lanes, quad, grp);
+            deblock_io_warp<false>(sm, descs, g, n_lanes, quad, grp, trace);
         else
-            deblock_io_warp<true>(sm, descs, g, n_lanes, quad, grp);
+            deblock_io_warp<true>(sm, descs, g, n_lanes, quad, grp, trace);
         return;
     }
     if (role == 0)
-        deblock_rows<false>(sm, descs, g, n_lanes, quad, grp);
+        deblock_rows<false>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
     else
-        deblock_rows<true>(sm, descs, g, n_lanes, quad, grp);
+        deblock_rows<true>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
+    if (times) g_dbf_cta_ns[tk][3] = dbf_now_ns();
     __syncthreads();  // lets the I/O warp publish the last row's final macroblock
 }
 #endif  // P264B200_DEFINE_KERNELS

@@ -84,6 +84,7 @@ struct p264b200_engine {
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {};
     bool groups_dirty = false;  // group streams hold work the main stream has not joined yet
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
+    int trace_ticket = -1;  // P264B200_TRACE: deblock CTA (by ticket) whose per-step cycle marks are recorded
 
     uint8_t *plane(int lane, int slot, int c) const
     {
@@ -233,6 +234,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!e) return P264B200_ENOMEM;
     e->cfg = *cfg;
     if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
+    if (const char *d = getenv("P264B200_TRACE")) e->trace_ticket = atoi(d);
     e->n_groups = 1;  // measured: overlapping groups does not pay while both kernels are ALU-issue bound
     if (const char *gq = getenv("P264B200_GROUPS")) e->n_groups = atoi(gq);
     if (e->n_groups < 1) e->n_groups = 1;
@@ -472,7 +474,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * (kDbfRows + 1), 0, st>>>(descs, g, nl, tickets + 1);
+            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * (kDbfRows + 1), 0, st>>>(descs, g, nl, tickets + 1, e->trace_ticket);
         }
         {
             ProfScope p(e, K_BORDER, st);
@@ -646,5 +648,21 @@ int p264b200_profile_read(p264b200_engine *e, float ms_out[8], uint64_t launches
     return P264B200_OK;
 }
 uint64_t p264b200_engine_launches(const p264b200_engine *e) { return e ? e->launches : 0; }
+
+int p264b200_debug_cta_times(void *dst, size_t bytes)
+{
+    if (!dst || bytes > sizeof(g_dbf_cta_ns)) return P264B200_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(dst, g_dbf_cta_ns, bytes));
+    return P264B200_OK;
+}
+
+int p264b200_debug_trace(void *dst, size_t bytes)
+{
+    if (!dst || bytes > sizeof(g_dbf_trace)) return P264B200_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(dst, g_dbf_trace, bytes));
+    return P264B200_OK;
+}
 
 }  // extern "C"
