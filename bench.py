@@ -63,11 +63,28 @@ def synth_kwargs(args, lane, rank):
 
 # ------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions.  NVML is polled every ~2 ms from a thread
+    (the device-resident leg lasts tens of milliseconds, too short for `nvidia-smi -lms`); `nvidia-smi` is the
+    fallback when the NVML binding is unusable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.samples, self.proc = [], None
+        self.samples, self.proc, self.nvml, self.mx, self.run = [], None, None, None, True
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = N.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.nvml = N
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,29 +93,51 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if not self.proc:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [l.split(", ") for t, l in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [l.split(", ") for _, l in self.samples[-3:]]
-        sm, reasons, mx = [], set(), None
-        for r in rows:
+    def _poll(self):
+        N = self.nvml
+        while self.run:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
+                sm = float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                try:
+                    bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.time(), sm, bits))
             except Exception:
                 pass
-        if not sm:
+            time.sleep(0.002)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            r = line.strip().split(", ")
+            try:
+                bits = 0
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        bits |= self.BITS[name]
+                self.mx = float(r[1])
+                self.samples.append((time.time(), float(r[0]), bits))
+            except Exception:
+                pass
+
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] wall-clock spans of the timed regions"""
+        self.run = False
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        if not self.nvml and not self.proc:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [(sm, b) for t, sm, b in self.samples if any(t0 - 0.005 <= t <= t1 + 0.005 for t0, t1 in windows)]
+        rows = inside or [(sm, b) for _, sm, b in self.samples[-3:]]
+        if not rows:
+            return None
+        bits = 0
+        for _, b in rows:
+            bits |= b
+        return {"sm_mhz": float(np.median([sm for sm, _ in rows])), "sm_max_mhz": self.mx,
+                "reasons": sorted(n for n, m in self.BITS.items() if bits & m), "samples": len(rows),
+                "source": "nvml" if self.nvml else "nvidia-smi", "in_timed_region": bool(inside)}
 
 
 # ------------------------------------------------------------------ CPU reference arm
@@ -308,7 +347,7 @@ def run_b200(args, rank, world, local_rank):
     launches = eng.launches - launches0
     prof = eng.profile_read()
     eng.profile_enable(False)
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clock_windows = [(t_wall0, t_wall1)]
 
     # ---- end-to-end leg through the C-ABI with host buffers
     e2e_ms, d2h_per_step = None, L * (16 * mb_w * 16 * mb_h * 3 // 2)
@@ -337,14 +376,16 @@ def run_b200(args, rank, world, local_rank):
             if rc:
                 raise RuntimeError(lib.p264b200_last_error().decode())
 
-        for i in range(max(1, min(args.warmup, 3))):
+        for i in range(args.warmup):
             e2e_step(i)
         barrier()
+        t_e0 = time.time()
         eng.timer_start()
-        n_e2e = max(2, min(args.steps, 10))
+        n_e2e = args.steps
         for i in range(n_e2e):
             e2e_step(args.warmup + i)
         e2e_total = eng.timer_stop()
+        clock_windows.append((t_e0, time.time()))
         barrier()
         e2e_ms = e2e_total / n_e2e
         assert "d" not in args.e2e_parts or int(out_host[:W].astype(np.int64).sum()) > 0
@@ -353,6 +394,7 @@ def run_b200(args, rank, world, local_rank):
     ms_step = ms / args.steps
     ms_step, e2e_max = reduce_max([ms_step, e2e_ms or 0.0], dist, "cuda")
     e2e_ms = e2e_max if e2e_ms is not None else None
+    clocks = sampler.stop(clock_windows) if sampler else None
     if rank != 0:
         if dist:
             dist.destroy_process_group()

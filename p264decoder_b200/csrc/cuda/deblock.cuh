@@ -162,17 +162,18 @@ __global__ void __launch_bounds__(256) deblock_bs_kernel(const FrameDesc *__rest
 }
 
 
-constexpr int kDbfRows = 8;     // macroblock rows (warps) per CTA
+constexpr int kDbfRows = 8;     // macroblock rows (filtering warps) per CTA
 constexpr int kDbfQuad = 4;     // lanes (streams) per warp, 8 threads each
-constexpr int kDbfRing = 4;     // hand-off slots per producer row (the consumer runs two macroblocks behind)
+constexpr int kDbfRing = 4;     // hand-off slots per producer row
 constexpr int kDbfTile = 272;   // bytes per (warp, stream) transpose tile: 16 rows x 16 B, + 16 B bank skew
 constexpr int kDbfSlot = 80;    // bytes per (slot, stream): 4 rows x 16 B, + 16 B bank skew
+constexpr int kDbfWarps = kDbfRows + 2;  // + the "in" and "out" warps that own the global progress words
 
-// Optional per-step cycle trace of ONE CTA (engine debug knob P264B200_TRACE=<ticket>): [warp][step][marks]:
-// 0 after the first barrier of a step, 1 before the second, 2 after it, 3 at the end of the step
+// Optional per-macroblock cycle trace of ONE CTA (engine debug knob P264B200_TRACE=<ticket>): [warp][x][marks]:
+// 0 top of the iteration, 1 before waiting for the rows above, 2 after that wait, 3 end of the iteration
 constexpr int kDbfTraceSteps = 320;
 __device__ long long g_dbf_trace[kDbfRows + 1][kDbfTraceSteps][6];
-__device__ long long g_dbf_cta_ns[2048][4];  // per ticket: %globaltimer at kernel entry, first step, last step, exit
+__device__ long long g_dbf_cta_ns[2048][4];  // per ticket: %globaltimer at kernel entry, first macroblock, last macroblock, exit (row warp 0)
 __device__ __forceinline__ long long dbf_now_ns()
 {
     long long t;
@@ -184,10 +185,52 @@ __device__ __forceinline__ void dbf_mark(bool on, int w, int s, int k)
     if (on && s < kDbfTraceSteps && (threadIdx.x & 31) == 0) g_dbf_trace[w][s][k] = clock64();
 }
 
+// ---- shared-memory transaction barriers (mbarrier), one arriving thread per phase -------------------
+// Slot k of a ring is used for macroblocks k, k + R, k + 2R, ...; use number n = x / R.  The consumer waits
+// on `full` with parity n & 1, the producer on `empty` with parity (n & 1) ^ 1 (passes at once for n = 0:
+// a fresh barrier reports its "previous" phase as complete).  arrive = release.cta, try_wait = acquire.cta.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DBF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DBF_DONE;\n"
+        "bra DBF_WAIT;\n"
+        "DBF_DONE:\n"
+        "}" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ int lds_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release(int *p, int v)
+{
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
 struct DbfSmem {
-    uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];              // luma: row r at 16r; chroma: plane p row r at 64p + 8r
-    uint8_t ring[kDbfRows][kDbfRing][kDbfQuad][kDbfSlot];    // luma: rows 12..15 at 16k; chroma: plane p rows 6,7 at 16p + 8k
-    uint8_t topring[kDbfRing][kDbfQuad][kDbfSlot];            // same layout: rows above warp 0, fetched from global memory by the I/O warp
+    uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];                  // luma: row r at 16r; chroma: plane p row r at 64p + 8r
+    uint8_t ring[kDbfRows + 1][kDbfRing][kDbfQuad][kDbfSlot];    // ring[0]: rows above warp 0 (filled by the in warp from global memory);
+                                                                 // ring[1 + w]: last rows of warp w's macroblocks.  luma: rows 12..15 at 16k;
+                                                                 // chroma: plane p rows 6,7 at 16p + 8k
+    uint64_t full[kDbfRows + 1][kDbfRing];                       // ring[i][k] holds the rows of its next macroblock
+    uint64_t empty[kDbfRows + 1][kDbfRing];                      // the consumer is done with ring[i][k]
+    int stored;                                                  // macroblocks of the CTA's last row that are in global memory
     int ticket;
 };
 
@@ -276,21 +319,22 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     constexpr int TR = C ? 2 : 4;    // rows handed down to the macroblock row below (per plane)
     constexpr int NP = 4 + 4 * NW;   // taps along a row incl. the 4 samples left of the macroblock
     constexpr int NQ = TR + NR;      // taps down a column incl. the rows above
+    constexpr int RM = kDbfRing - 1;
     typedef typename DbfVec<NW>::type Vec;
     using swar::prmt;
 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, t = lane & 7;
     const int pl = C ? t >> 2 : 0, j = C ? t & 3 : t;  // plane; row pair (vertical edges) = column pair (horizontal edges)
     const int row = grp * kDbfRows + w;
-    const bool row_ok = row < g.mb_h;
+    if (row >= g.mb_h) return;       // nobody waits for a row outside the picture
     const bool has_top = row > 0;
-    const bool top_smem = w > 0;
-    const bool bottom_smem = w + 1 < kDbfRows && row + 1 < g.mb_h;
+    const bool bottom_smem = w + 1 < kDbfRows && row + 1 < g.mb_h;     // the row below is a warp of this CTA
+    const bool publishes = w + 1 == kDbfRows && row + 1 < g.mb_h;      // ... or the first row of the next CTA
     const int stream = kDbfQuad * quad + sub;
     const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
-    const bool act = row_ok && stream < n_lanes && fd.deblock != 0;
+    const bool act = stream < n_lanes && fd.deblock != 0;
     const int stride = C ? g.c_stride : g.y_stride;
-    // this thread's two sample rows, and (threads 0..3) the row above it moves between global and shared memory:
+    // this thread's two sample rows, and (threads 0..3) the row above it moves from shared to global memory:
     // luma row -4 + t; chroma plane t >> 1, row -2 + (t & 1)
     uint8_t *grow = fd.cur[C ? 1 + pl : 0] + (ptrdiff_t)(NR * row + 2 * j) * stride;
     uint8_t *gtop = C ? fd.cur[1 + ((t >> 1) & 1)] + (ptrdiff_t)(NR * row - 2 + (t & 1)) * stride : fd.cur[0] + (ptrdiff_t)(NR * row - 4 + (t & 3)) * stride;
@@ -314,96 +358,100 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         prm = __ldg(reinterpret_cast<const uint4 *>(C ? side[0].chroma : side[0].luma));
     }
 
-    // Lockstep schedule, one-macroblock lag: step s = [barrier] vertical edges of MB (s - w) [barrier] horizontal
-    // edges of MB (s - w).  The left-edge filter of MB x+1 finalises the last columns of MB x in the first half of
-    // a step, so the row below can filter the top edge of its MB x in the second half of the same step.
-    const int n_steps = g.mb_w + (kDbfRows - 1);
+    // Macroblock m of this row is final except for what the row below does to its last rows: store it, and
+    // pass those rows down (shared-memory ring inside the CTA, global memory + the out warp across CTAs).
+    auto hand_off = [&](int m) {
+        Vec va, vb;
+        vec_set(va, prev[0]);
+        vec_set(vb, prev[1]);
+        if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * m) = va;
+        if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * m) = vb;
+        if (bottom_smem) {
+            mbar_wait(&sm.empty[w + 1][m & RM], ((m / kDbfRing) & 1) ^ 1);
+            if (to_ring) {
+                uint8_t *slot = sm.ring[w + 1][m & RM][sub] + ring_off;
+                *reinterpret_cast<Vec *>(slot) = va;
+                *reinterpret_cast<Vec *>(slot + RB) = vb;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.full[w + 1][m & RM]);
+        } else if (publishes) {
+            __syncwarp();
+            if (lane == 0) sts_release(&sm.stored, m + 1);
+        }
+    };
+
+    // Each warp runs at its own pace; the only cross-warp dependency is the top edge of macroblock x, which needs
+    // the last rows of macroblock x of the row above AFTER the left edge of its macroblock x+1 (a one-macroblock lag).
 #pragma unroll 1
-    for (int s = 0; s < n_steps; s++) {
-        const int x = s - w;
-        const bool on = x >= 0 && x < g.mb_w && row_ok;
+    for (int x = 0; x < g.mb_w; x++) {
         const bool last = x == g.mb_w - 1;
-        dbf_mark(trace, w, s, 3);
-        __syncthreads();
-        dbf_mark(trace, w, s, 0);
-        if (times_on && threadIdx.x == 0 && (s == 0 || s == n_steps - 1)) g_dbf_cta_ns[tk][s == 0 ? 1 : 2] = dbf_now_ns();
-        if (on) {
-            // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull
-            // the next line into L2 so that those loads do not wait on HBM inside the dependent chain)
-            if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + RB * x + 128));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + stride + RB * x + 128));
-            }
-            if (act && !last) {
-                bsw_n = ldg_now_u32(&side[x + 1].bs[j >> (C ? 0 : 1)]);
-                {
-                    // (two loads with no unused component: the register of an unused one would be recycled as scratch
-                    // while the prefetch is still in flight, and that write has to wait out the whole memory latency)
-                    const uint32_t *pp = C ? side[x + 1].chroma : side[x + 1].luma;
-                    const uint2 xy = ldg_now_v2(pp);
-                    prm_n.x = xy.x, prm_n.y = xy.y, prm_n.z = ldg_now_u32(pp + 2);
-                }
-                // (this row's samples were written by the previous kernel; nobody else touches them before we do)
-                Vec va, vb;
-                ldg_now(grow + RB * (x + 1), va);
-                ldg_now(grow + stride + RB * (x + 1), vb);
-                vec_get(va, nxt[0]);
-                vec_get(vb, nxt[1]);
-            }
-            // ---- vertical edges: taps of this thread's two rows, two rows per register
+        dbf_mark(trace, w, x, 0);
+        if (times_on && threadIdx.x == 0 && (x == 0 || last)) g_dbf_cta_ns[tk][x == 0 ? 1 : 2] = dbf_now_ns();
+        // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull
+        // the next line into L2 so that those loads do not wait on HBM inside the dependent chain)
+        if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + RB * x + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + stride + RB * x + 128));
+        }
+        if (act && !last) {
+            bsw_n = ldg_now_u32(&side[x + 1].bs[j >> (C ? 0 : 1)]);
             {
-                uint32_t P[NP];
+                // (two loads with no unused component: the register of an unused one would be recycled as scratch
+                // while the prefetch is still in flight, and that write has to wait out the whole memory latency)
+                const uint32_t *pp = C ? side[x + 1].chroma : side[x + 1].luma;
+                const uint2 xy = ldg_now_v2(pp);
+                prm_n.x = xy.x, prm_n.y = xy.y, prm_n.z = ldg_now_u32(pp + 2);
+            }
+            // (this row's samples were written by the previous kernel; nobody else touches them before we do)
+            Vec va, vb;
+            ldg_now(grow + RB * (x + 1), va);
+            ldg_now(grow + stride + RB * (x + 1), vb);
+            vec_get(va, nxt[0]);
+            vec_get(vb, nxt[1]);
+        }
+        // ---- vertical edges: taps of this thread's two rows, two rows per register
+        {
+            uint32_t P[NP];
 #pragma unroll
-                for (int wd = 0; wd < 1 + NW; wd++) {
-                    const uint32_t wa = wd == 0 ? prev[0][NW - 1] : cur[0][wd - 1], wb = wd == 0 ? prev[1][NW - 1] : cur[1][wd - 1];
-                    const uint32_t t01 = prmt(wa, wb, 0x5140), t23 = prmt(wa, wb, 0x7362);
-                    P[4 * wd + 0] = prmt(t01, 0, 0x4140);
-                    P[4 * wd + 1] = prmt(t01, 0, 0x4342);
-                    P[4 * wd + 2] = prmt(t23, 0, 0x4140);
-                    P[4 * wd + 3] = prmt(t23, 0, 0x4342);
-                }
-                const DbfDir dv = dbf_dir(prm.x, prm.z);
-                if (C)
-                    dbf_chroma_dir(P + 2, bsw & 0xf, (bsw >> 16) & 0xf, dv);
+            for (int wd = 0; wd < 1 + NW; wd++) {
+                const uint32_t wa = wd == 0 ? prev[0][NW - 1] : cur[0][wd - 1], wb = wd == 0 ? prev[1][NW - 1] : cur[1][wd - 1];
+                const uint32_t t01 = prmt(wa, wb, 0x5140), t23 = prmt(wa, wb, 0x7362);
+                P[4 * wd + 0] = prmt(t01, 0, 0x4140);
+                P[4 * wd + 1] = prmt(t01, 0, 0x4342);
+                P[4 * wd + 2] = prmt(t23, 0, 0x4140);
+                P[4 * wd + 3] = prmt(t23, 0, 0x4342);
+            }
+            const DbfDir dv = dbf_dir(prm.x, prm.z);
+            if (C)
+                dbf_chroma_dir(P + 2, bsw & 0xf, (bsw >> 16) & 0xf, dv);
+            else
+                dbf_luma_dir(P, bsw & 0x0f0f0f0fu, dv);
+#pragma unroll
+            for (int wd = 0; wd < 1 + NW; wd++) {
+                const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
+                const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
+                if (wd == 0)
+                    prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
                 else
-                    dbf_luma_dir(P, bsw & 0x0f0f0f0fu, dv);
-#pragma unroll
-                for (int wd = 0; wd < 1 + NW; wd++) {
-                    const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
-                    const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
-                    if (wd == 0)
-                        prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
-                    else
-                        cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
-                }
-            }
-            // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
-            if (x > 0) {
-                Vec va, vb;
-                vec_set(va, prev[0]);
-                vec_set(vb, prev[1]);
-                if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * (x - 1)) = va;
-                if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * (x - 1)) = vb;
-                if (to_ring) {
-                    uint8_t *slot = sm.ring[w][(x - 1) & (kDbfRing - 1)][sub] + ring_off;
-                    *reinterpret_cast<Vec *>(slot) = va;
-                    *reinterpret_cast<Vec *>(slot + RB) = vb;
-                }
-            }
-            // ---- transpose through shared memory: rows in, 16-bit column pairs out
-            {
-                Vec va, vb;
-                vec_set(va, cur[0]);
-                vec_set(vb, cur[1]);
-                *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
-                *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
+                    cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
             }
         }
-        dbf_mark(trace, w, s, 1);
-        __syncthreads();
-        dbf_mark(trace, w, s, 2);
-        if (!on) continue;
-        uint8_t *slot_top = top_smem ? sm.ring[w - 1][x & (kDbfRing - 1)][sub] : sm.topring[x & (kDbfRing - 1)][sub];
+        // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
+        if (x > 0) hand_off(x - 1);
+        // ---- transpose through shared memory: rows in, 16-bit column pairs out
+        {
+            Vec va, vb;
+            vec_set(va, cur[0]);
+            vec_set(vb, cur[1]);
+            *reinterpret_cast<Vec *>(T + RB * (2 * j)) = va;
+            *reinterpret_cast<Vec *>(T + RB * (2 * j + 1)) = vb;
+        }
+        __syncwarp();
+        dbf_mark(trace, w, x, 1);
+        if (has_top) mbar_wait(&sm.full[w][x & RM], (x / kDbfRing) & 1);
+        dbf_mark(trace, w, x, 2);
+        uint8_t *slot_top = sm.ring[w][x & RM][sub];
         uint8_t *topp = slot_top + (C ? 16 * pl : 0);
         {
             uint32_t Q[NQ];
@@ -433,19 +481,22 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         vec_get(*reinterpret_cast<const Vec *>(T + RB * (2 * j)), prev[0]);
         vec_get(*reinterpret_cast<const Vec *>(T + RB * (2 * j + 1)), prev[1]);
         // the rows above are finished: luma rows -3..-1, chroma row -1 (rows -4 / -2 are only read)
-        if (has_top && act && t < 4 && (C ? (t & 1) : (t != 0)))
-            *reinterpret_cast<Vec *>(gtop + RB * x) = *reinterpret_cast<const Vec *>(slot_top + top_off);
-        if (last) {
-            Vec va, vb;
-            vec_set(va, prev[0]);
-            vec_set(vb, prev[1]);
-            if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * x) = va;
-            if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * x) = vb;
-            if (to_ring) {
-                uint8_t *slot = sm.ring[w][x & (kDbfRing - 1)][sub] + ring_off;
-                *reinterpret_cast<Vec *>(slot) = va;
-                *reinterpret_cast<Vec *>(slot + RB) = vb;
-            }
+        if (has_top) {
+            if (act && t < 4 && (C ? (t & 1) : (t != 0))) *reinterpret_cast<Vec *>(gtop + RB * x) = *reinterpret_cast<const Vec *>(slot_top + top_off);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[w][x & RM]);
+        }
+        if (last) hand_off(x);
+        dbf_mark(trace, w, x, 3);
+        if (trace) {
+            // diagnostics only: split the wait for the prefetched side info from the wait for the prefetched rows
+            uint32_t d;
+            asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(bsw_n), "r"(prm_n.x ^ prm_n.z));
+            if (d == 0x12345678u) g_dbf_trace[0][0][5] = d;
+            dbf_mark(trace, w, x, 4);
+            asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(nxt[0][0]), "r"(nxt[1][NW - 1]));
+            if (d == 0x12345678u) g_dbf_trace[0][0][5] = d;
+            dbf_mark(trace, w, x, 5);
         }
 #pragma unroll
         for (int k = 0; k < NW; k++) cur[0][k] = nxt[0][k], cur[1][k] = nxt[1][k];
@@ -454,92 +505,85 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     }
 }
 
-// The I/O warp of a CTA (warp kDbfRows): everything that touches the global progress words, so that no
-// filtering warp ever executes a fence or polls.  Per lockstep step s it
-//  * (consumer side, row group > 0) keeps the rows above warp 0 two macroblocks ahead in sm.topring: waits for
-//    the row group above to have stored macroblock s+2, loads its last rows, and drops them into the ring one
-//    step later (warp 0 reads slot s at step s);
-//  * (producer side) publishes how many macroblocks of the CTA's last row are in global memory.  The barrier
-//    orders that row's stores before this warp's fence + release (fence cumulativity), one step behind.
+// The "in" warp of a CTA (row group > 0): keeps ring[0] -- the rows above warp 0, which the row group above
+// stored to global memory -- up to kDbfRing macroblocks ahead of warp 0.  It alone polls the global progress
+// word of the row above, so no filtering warp ever spins on global memory.
 template <bool C>
-__device__ __forceinline__ void deblock_io_warp(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
-                                                int grp, bool trace)
+__device__ __forceinline__ void deblock_in_warp(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
+                                                int grp)
 {
-    constexpr int RB = C ? 8 : 16, NR = C ? 8 : 16;
+    constexpr int RB = C ? 8 : 16, NR = C ? 8 : 16, RM = kDbfRing - 1;
     typedef typename DbfVec<RB / 4>::type Vec;
     const int lane = threadIdx.x & 31, sub = (lane >> 2) & 3, k = lane & 3;  // lanes 0..15: (stream, row above)
     const int row0 = grp * kDbfRows;                 // first macroblock row of the CTA
-    const int last_w = kDbfRows - 1, row_last = row0 + last_w;
-    const bool consumer = grp > 0, producer = row_last + 1 < g.mb_h;
     const int stream = kDbfQuad * quad + sub;
     const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
     const bool act = lane < 16 && stream < n_lanes && fd.deblock != 0;
-    int *prog = descs[kDbfQuad * quad].row_progress + (C ? 2 : 1) * g.mb_h;  // one progress word per (quad, role, row)
+    const int *prog = descs[kDbfQuad * quad].row_progress + (C ? 2 : 1) * g.mb_h + row0 - 1;  // one progress word per (quad, role, row)
     const int stride = C ? g.c_stride : g.y_stride;
     // luma: row -4 + k; chroma: plane k >> 1, row -2 + (k & 1)
     const uint8_t *gtop = C ? fd.cur[1 + (k >> 1)] + (ptrdiff_t)(NR * row0 - 2 + (k & 1)) * stride : fd.cur[0] + (ptrdiff_t)(NR * row0 - 4 + k) * stride;
     const int top_off = C ? 16 * (k >> 1) + 8 * (k & 1) : 16 * k;
     int seen = 0;
-    auto wait_for = [&](int need) {
-        if (seen < need) {
+#pragma unroll 1
+    for (int x = 0; x < g.mb_w; x++) {
+        if (seen <= x) {
             if (lane == 0) {
+                // relaxed polls (an acquire load invalidates the SM's whole L1 on every spin), one fence on success
                 int spins = 0;
-                while ((seen = ld_acquire(prog + row0 - 1)) < need) __nanosleep(++spins < 16 ? 40 : 400);
+                while ((seen = ld_relaxed(prog)) <= x) __nanosleep(++spins < 8 ? 100 : 400);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
             }
+            __syncwarp();   // orders the other lanes' loads after lane 0's fence
             seen = __shfl_sync(0xffffffffu, seen, 0);
         }
-    };
-    Vec pend;
-    {
-        uint32_t z[4] = {0, 0, 0, 0};
-        vec_set(pend, z);
+        Vec v;
+        {
+            uint32_t z[4] = {0, 0, 0, 0};
+            vec_set(v, z);
+        }
+        if (act) v = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * x));
+        mbar_wait(&sm.empty[0][x & RM], ((x / kDbfRing) & 1) ^ 1);
+        if (act) *reinterpret_cast<Vec *>(sm.ring[0][x & RM][sub] + top_off) = v;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.full[0][x & RM]);
     }
-    if (consumer) {
-        // macroblocks 0 and 1 before the first step
-        wait_for(min(2, g.mb_w));
-        if (act) {
-            *reinterpret_cast<Vec *>(sm.topring[0][sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop));
-            if (g.mb_w > 1) *reinterpret_cast<Vec *>(sm.topring[1][sub] + top_off) = __ldcg(reinterpret_cast<const Vec *>(gtop + RB));
-        }
-    }
-    const int n_steps = g.mb_w + (kDbfRows - 1);
-    int peek = 0;  // progress word read asynchronously during the previous step
-#pragma unroll 1
-    for (int s = 0; s <= n_steps; s++) {
-        dbf_mark(trace, kDbfRows, s, 3);
-        __syncthreads();  // s == n_steps: the extra barrier after the loop of the filtering warps
-        dbf_mark(trace, kDbfRows, s, 0);
-        if (consumer && s >= 1 && s + 1 < g.mb_w && act) *reinterpret_cast<Vec *>(sm.topring[(s + 1) & (kDbfRing - 1)][sub] + top_off) = pend;
-        if (producer) {
-            // the last row worked on macroblock x7 during step s-1: macroblocks [0, x7) are stored, all after the last.
-            // (before this step's loads are issued, so that the fence does not wait for them)
-            const int x7 = s - 1 - last_w;
-            if (x7 >= 1 && x7 < g.mb_w && lane == 0) {
-                __threadfence();
-                st_release(prog + row_last, x7 == g.mb_w - 1 ? g.mb_w : x7);
-            }
-        }
-        if (consumer && s + 2 < g.mb_w) {
-            seen = max(seen, __shfl_sync(0xffffffffu, peek, 0));
-            wait_for(min(s + 3, g.mb_w));  // normally satisfied by the value peeked one step ago
-            __threadfence();               // acquire side for the peeked (relaxed) value
-            if (act) pend = __ldcg(reinterpret_cast<const Vec *>(gtop + RB * (s + 2)));
-            if (lane == 0) peek = ld_relaxed(prog + row0 - 1);
-        }
-        if (s < n_steps) {
-            dbf_mark(trace, kDbfRows, s, 1);
-            __syncthreads();
-            dbf_mark(trace, kDbfRows, s, 2);
-        }
+}
+
+// The "out" thread of a CTA that has a row group below it: publishes how many macroblocks of the CTA's last row
+// are in global memory.  The last row's lanes store, __syncwarp, lane 0 releases sm.stored (cta scope); this
+// thread acquires it, fences at gpu scope and releases the progress word (cumulativity carries the stores).
+__device__ __forceinline__ void deblock_out_thread(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int quad, int grp, bool chroma)
+{
+    const int row_last = grp * kDbfRows + kDbfRows - 1;
+    if (row_last + 1 >= g.mb_h) return;
+    int *prog = descs[kDbfQuad * quad].row_progress + (chroma ? 2 : 1) * g.mb_h + row_last;
+    int published = 0, spins = 0;
+    while (published < g.mb_w) {
+        const int c = lds_acquire(&sm.stored);
+        if (c > published) {
+            st_release(prog, c);   // release.gpu is cumulative over what the acquire above made visible
+            published = c;
+            spins = 0;
+        } else
+            __nanosleep(++spins < 8 ? 100 : 300);
     }
 }
 
 // grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
 // dependency order (the group above of the same quad and role always has a smaller ticket)
-__global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int trace_ticket)
+__global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int trace_ticket)
 {
     __shared__ __align__(16) DbfSmem sm;
-    if (threadIdx.x == 0) sm.ticket = atomicAdd(ticket, 1);
+    if (threadIdx.x == 0) {
+        sm.ticket = atomicAdd(ticket, 1);
+        sm.stored = 0;
+        for (int i = 0; i < (kDbfRows + 1) * kDbfRing; i++) {
+            mbar_init(&sm.full[0][0] + i, 1);
+            mbar_init(&sm.empty[0][0] + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int tk = sm.ticket;
     const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
@@ -548,11 +592,18 @@ __global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const F
     const bool trace = tk == trace_ticket;
     const bool times = trace_ticket >= 0 && tk < 2048 && threadIdx.x == 0;
     if (times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
-    if (threadIdx.x >= 32 * kDbfRows) {
-        if (role == 0)
-            deblock_io_warp<false>(sm, descs, g, n_lanes, quad, grp, trace);
-        else
-            deblock_io_warp<true>(sm, descs, g, n_lanes, quad, grp, trace);
+    const int w = threadIdx.x >> 5;
+    if (w == kDbfRows) {
+        if (grp > 0) {
+            if (role == 0)
+                deblock_in_warp<false>(sm, descs, g, n_lanes, quad, grp);
+            else
+                deblock_in_warp<true>(sm, descs, g, n_lanes, quad, grp);
+        }
+        return;
+    }
+    if (w == kDbfRows + 1) {
+        if ((threadIdx.x & 31) == 0) deblock_out_thread(sm, descs, g, quad, grp, role != 0);
         return;
     }
     if (role == 0)
@@ -560,7 +611,6 @@ __global__ void __launch_bounds__(32 * (kDbfRows + 1), 2) deblock_kernel(const F
     else
         deblock_rows<true>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
     if (times) g_dbf_cta_ns[tk][3] = dbf_now_ns();
-    __syncthreads();  // lets the I/O warp publish the last row's final macroblock
 }
 #endif  // P264B200_DEFINE_KERNELS
 

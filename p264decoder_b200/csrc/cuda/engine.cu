@@ -474,7 +474,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * (kDbfRows + 1), 0, st>>>(descs, g, nl, tickets + 1, e->trace_ticket);
+            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, 0, st>>>(descs, g, nl, tickets + 1, e->trace_ticket);
         }
         {
             ProfScope p(e, K_BORDER, st);
