@@ -167,6 +167,7 @@ constexpr int kDbfQuad = 4;     // lanes (streams) per warp, 8 threads each
 constexpr int kDbfRing = 4;     // hand-off slots per producer row
 constexpr int kDbfTile = 272;   // bytes per (warp, stream) transpose tile: 16 rows x 16 B, + 16 B bank skew
 constexpr int kDbfSlot = 80;    // bytes per (slot, stream): 4 rows x 16 B, + 16 B bank skew
+constexpr int kDbfSmSlots = 256;  // per-SM arrival counters (indexed by %smid) behind the tickets
 constexpr int kDbfWarps = kDbfRows + 2;  // + the "in" and "out" warps that own the global progress words
 
 // Optional per-macroblock cycle trace of ONE CTA (engine debug knob P264B200_TRACE=<ticket>): [warp][x][marks]:
@@ -570,13 +571,27 @@ __device__ __forceinline__ void deblock_out_thread(DbfSmem &sm, const FrameDesc 
     }
 }
 
-// grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups, handed out by ticket in
-// dependency order (the group above of the same quad and role always has a smaller ticket)
-__global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int trace_ticket)
+// grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups.  A CTA draws its work at run time:
+//  * the role from its arrival order on its SM (first luma, second chroma, ...), so that co-resident CTAs are
+//    one luma + one chroma -- luma is the heavier role, and two luma CTAs on one SM would pace every chain below them;
+//  * (quad, row group) from a per-role ticket in dependency order (the group above of the same quad and role
+//    always has a smaller ticket, i.e. is resident or finished).  A role whose tickets are used up falls back to the other.
+// sync: [0] intra ticket (other kernel), [1] luma ticket, [2] chroma ticket, [4 + smid] arrivals per SM
+__global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *sync, int trace_ticket)
 {
     __shared__ __align__(16) DbfSmem sm;
+    const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
     if (threadIdx.x == 0) {
-        sm.ticket = atomicAdd(ticket, 1);
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int per_role = (int)(gridDim.x >> 1);
+        int role = atomicAdd(sync + 4 + (smid & (kDbfSmSlots - 1)), 1) & 1;
+        int u = atomicAdd(sync + 1 + role, 1);
+        if (u >= per_role) {
+            role ^= 1;
+            u = atomicAdd(sync + 1 + role, 1);
+        }
+        sm.ticket = 2 * u + role;
         sm.stored = 0;
         for (int i = 0; i < (kDbfRows + 1) * kDbfRing; i++) {
             mbar_init(&sm.full[0][0] + i, 1);
@@ -586,7 +601,6 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
     }
     __syncthreads();
     const int tk = sm.ticket;
-    const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
     const int role = tk & 1, u = tk >> 1;
     const int quad = u / groups, grp = u % groups;
     const bool trace = tk == trace_ticket;

@@ -64,7 +64,7 @@ struct p264b200_engine {
     PackSrc *d_pack = nullptr;     // [lanes][n_slots] plane origins
     DeblockSide *d_bs = nullptr;   // [lanes][n_mb]
     uint32_t *d_dqp = nullptr;     // [lanes][n_mb]
-    int *d_sync = nullptr;  // [4 tickets/pad][lanes][3*mb_h]: intra, luma deblock, chroma deblock wavefronts
+    int *d_sync = nullptr;  // [groups][kSyncHdr] tickets + per-SM arrival counters, then [lanes][3*mb_h]: intra, luma deblock, chroma deblock wavefronts
     size_t sync_bytes = 0;
     std::vector<uint8_t> slot_flags;  // [step][lane]: bit0 intra MBs present, bit1 deblock on, bit2 P slice
     // timing
@@ -79,6 +79,7 @@ struct p264b200_engine {
     // lane groups: independent lanes are split over `n_groups` CUDA streams so that one group's
     // latency-bound wavefront kernels overlap with another group's MC kernel on the same SMs
     static constexpr int kMaxGroups = 8;
+    static constexpr int kSyncHdr = 4 + kDbfSmSlots;  // per lane group: intra ticket, luma / chroma deblock tickets, pad, per-SM arrival counters
     int n_groups = 1;
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {};
@@ -256,7 +257,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     e->coef_cap = (e->coef_cap + 7) & ~(size_t)7;
     const size_t frames = (size_t)cfg->lanes * cfg->n_slots;
     const size_t slots = (size_t)cfg->stage_steps * cfg->lanes;
-    e->sync_bytes = (4 * p264b200_engine::kMaxGroups + (size_t)cfg->lanes * 3 * g.mb_h) * sizeof(int);
+    e->sync_bytes = ((size_t)p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)cfg->lanes * 3 * g.mb_h) * sizeof(int);
     int rc = P264B200_OK;
     auto fail = [&](const char *what, cudaError_t err) {
         set_err(what, err);
@@ -345,7 +346,7 @@ int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_sy
     for (int c = 0; c < 3; c++) d.cur[c] = e->plane(lane, h.dst_slot, c);
     for (int i = 0; i < h.num_ref; i++)
         for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
-    d.row_progress = e->d_sync + 4 * p264b200_engine::kMaxGroups + (size_t)lane * 3 * g.mb_h;
+    d.row_progress = e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)lane * 3 * g.mb_h;
     d.dbf_bs = e->d_bs + (size_t)lane * n_mb;
     d.dbf_qp = e->d_dqp + (size_t)lane * n_mb;
     d.slice_type = h.slice_type;
@@ -447,8 +448,8 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         if (G > 1) {
             CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
             // wavefront state of this group's lanes + its tickets
-            CK(cudaMemsetAsync(e->d_sync + 4 * gi, 0, 4 * sizeof(int), st));
-            CK(cudaMemsetAsync(e->d_sync + 4 * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), st));
+            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * gi, 0, p264b200_engine::kSyncHdr * sizeof(int), st));
+            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), st));
             // stagger: this group's MC starts when the previous group's MC is done, so that MC (issue-bound)
             // of one group overlaps the latency-bound wavefronts of the others instead of all groups moving in phase
             if (gi > 0) CK(cudaStreamWaitEvent(st, e->ev_mc[gi - 1], 0));
@@ -457,7 +458,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         for (int l = l0; l < l1; l++) flags |= e->slot_flags[(size_t)step * e->cfg.lanes + l];
         const bool intra = flags & 1, dbf = flags & 2, pslice = flags & 4;
         const FrameDesc *descs = descs0 + l0;
-        int *tickets = e->d_sync + 4 * gi;
+        int *tickets = e->d_sync + p264b200_engine::kSyncHdr * gi;
         if (pslice) {
             ProfScope p(e, K_INTER, st);
             const int tiles_x = (g.mb_w + kTileW - 1) / kTileW, tiles_y = (g.mb_h + kTileH - 1) / kTileH;
@@ -474,7 +475,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, 0, st>>>(descs, g, nl, tickets + 1, e->trace_ticket);
+            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, 0, st>>>(descs, g, nl, tickets, e->trace_ticket);
         }
         {
             ProfScope p(e, K_BORDER, st);
