@@ -263,13 +263,14 @@ __device__ __forceinline__ swar::EdgeK dbf_edge_k(const DbfDir &d, bool mb_edge,
     return k;
 }
 
-// The four luma edges of one direction on two lines, v = 4 samples before the macroblock + its 16 samples.
-// bs4: bS of edge e in bits 8e..8e+3.  The bS < 4 filters are straight-line code with no votes or branches
-// between the edges, so the instruction scheduler can overlap them (edge e+1 needs edge e only through one tap).
-__device__ __forceinline__ void dbf_luma_dir(uint32_t *v, uint32_t bs4, const DbfDir &d)
+// The four luma edges of one direction on two lines, v = 4 samples before the macroblock + its 16 samples, split
+// into the macroblock edge (after which the neighbouring macroblock is final and can be handed on) and the three
+// inner edges.  bs4: bS of edge e in bits 8e..8e+3.  The bS < 4 filters are straight-line code with no votes or
+// branches between the edges, so the instruction scheduler can overlap them (edge e+1 needs edge e only through one tap).
+__device__ __forceinline__ void dbf_luma_edge0(uint32_t *v, uint32_t bs4, const DbfDir &d)
 {
-    if (!__any_sync(0xffffffffu, bs4 != 0)) return;
     const int bs0 = bs4 & 0xf;
+    if (!__any_sync(0xffffffffu, bs0 != 0)) return;
     if (__any_sync(0xffffffffu, bs0 == 4)) {
         // intra macroblock edge: the strong filter, only on the lines that have bS 4 (the normal one is off there)
         const int alpha = d.prm_mb & 0xff;
@@ -277,26 +278,37 @@ __device__ __forceinline__ void dbf_luma_dir(uint32_t *v, uint32_t bs4, const Db
         k4.n_alpha = bs0 == 4 ? d.na_mb : 0u, k4.n_beta = d.nb_mb, k4.tc0 = 0;
         swar::luma_strong(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], k4, alpha);
     }
+    const swar::EdgeK k = dbf_edge_k(d, true, bs0, true);
+    swar::luma_normal(v[1], v[2], v[3], v[4], v[5], v[6], k);
+}
+__device__ __forceinline__ void dbf_luma_inner(uint32_t *v, uint32_t bs4, const DbfDir &d)
+{
+    if (!__any_sync(0xffffffffu, (bs4 & 0x0f0f0f00u) != 0)) return;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const swar::EdgeK k = dbf_edge_k(d, e == 0, (bs4 >> (8 * e)) & 0xf, true);
+    for (int e = 1; e < 4; e++) {
+        const swar::EdgeK k = dbf_edge_k(d, false, (bs4 >> (8 * e)) & 0xf, true);
         swar::luma_normal(v[4 * e + 1], v[4 * e + 2], v[4 * e + 3], v[4 * e + 4], v[4 * e + 5], v[4 * e + 6], k);
     }
 }
 // The two chroma edges of one direction on two lines, v = p1 p0 | q0 q1 . . q0' q1' ...: edge 0 at v[2], edge 2 at v[6]
-__device__ __forceinline__ void dbf_chroma_dir(uint32_t *v, int bs0, int bs2, const DbfDir &d)
+__device__ __forceinline__ void dbf_chroma_edge0(uint32_t *v, int bs0, const DbfDir &d)
 {
-    if (!__any_sync(0xffffffffu, (bs0 | bs2) != 0)) return;
-    const swar::EdgeK k0 = dbf_edge_k(d, true, bs0, false), k2 = dbf_edge_k(d, false, bs2, false);
+    if (!__any_sync(0xffffffffu, bs0 != 0)) return;
+    const swar::EdgeK k0 = dbf_edge_k(d, true, bs0, false);
     uint32_t p0 = v[1], q0 = v[2];
     swar::chroma_edge2(v[0], p0, q0, v[3], k0, false);
-    swar::chroma_edge2(v[4], v[5], v[6], v[7], k2, false);
     if (__any_sync(0xffffffffu, bs0 == 4)) {
         uint32_t sp0 = v[1], sq0 = v[2];
         swar::chroma_edge2(v[0], sp0, sq0, v[3], k0, true);
         if (bs0 == 4) p0 = sp0, q0 = sq0;
     }
     v[1] = p0, v[2] = q0;
+}
+__device__ __forceinline__ void dbf_chroma_inner(uint32_t *v, int bs2, const DbfDir &d)
+{
+    if (!__any_sync(0xffffffffu, bs2 != 0)) return;
+    const swar::EdgeK k2 = dbf_edge_k(d, false, bs2, false);
+    swar::chroma_edge2(v[4], v[5], v[6], v[7], k2, false);
 }
 
 template <int N> struct DbfVec;
@@ -411,7 +423,8 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
             vec_get(va, nxt[0]);
             vec_get(vb, nxt[1]);
         }
-        // ---- vertical edges: taps of this thread's two rows, two rows per register
+        // ---- vertical edges: taps of this thread's two rows, two rows per register.  The macroblock edge goes first:
+        // it finalises the previous macroblock (its last columns), whose hand-off is what the row below waits for.
         {
             uint32_t P[NP];
 #pragma unroll
@@ -425,21 +438,24 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
             }
             const DbfDir dv = dbf_dir(prm.x, prm.z);
             if (C)
-                dbf_chroma_dir(P + 2, bsw & 0xf, (bsw >> 16) & 0xf, dv);
+                dbf_chroma_edge0(P + 2, bsw & 0xf, dv);
             else
-                dbf_luma_dir(P, bsw & 0x0f0f0f0fu, dv);
+                dbf_luma_edge0(P, bsw & 0x0f0f0f0fu, dv);
+            {
+                const uint32_t t01 = prmt(P[0], P[1], 0x6240), t23 = prmt(P[2], P[3], 0x6240);
+                prev[0][NW - 1] = prmt(t01, t23, 0x5410), prev[1][NW - 1] = prmt(t01, t23, 0x7632);
+            }
+            if (x > 0) hand_off(x - 1);
+            if (C)
+                dbf_chroma_inner(P + 2, (bsw >> 16) & 0xf, dv);
+            else
+                dbf_luma_inner(P, bsw & 0x0f0f0f0fu, dv);
 #pragma unroll
-            for (int wd = 0; wd < 1 + NW; wd++) {
+            for (int wd = 1; wd < 1 + NW; wd++) {
                 const uint32_t t01 = prmt(P[4 * wd + 0], P[4 * wd + 1], 0x6240), t23 = prmt(P[4 * wd + 2], P[4 * wd + 3], 0x6240);
-                const uint32_t wa = prmt(t01, t23, 0x5410), wb = prmt(t01, t23, 0x7632);
-                if (wd == 0)
-                    prev[0][NW - 1] = wa, prev[1][NW - 1] = wb;
-                else
-                    cur[0][wd - 1] = wa, cur[1][wd - 1] = wb;
+                cur[0][wd - 1] = prmt(t01, t23, 0x5410), cur[1][wd - 1] = prmt(t01, t23, 0x7632);
             }
         }
-        // ---- the previous macroblock's rows are final now (its last columns just saw this left edge)
-        if (x > 0) hand_off(x - 1);
         // ---- transpose through shared memory: rows in, 16-bit column pairs out
         {
             Vec va, vb;
@@ -463,13 +479,15 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
             }
             const DbfDir dh = dbf_dir(prm.y, prm.z);
             if (C) {
-                dbf_chroma_dir(Q, (bsw >> 4) & 0xf, (bsw >> 20) & 0xf, dh);
+                dbf_chroma_edge0(Q, (bsw >> 4) & 0xf, dh);
+                dbf_chroma_inner(Q, (bsw >> 20) & 0xf, dh);
                 if (has_top) *reinterpret_cast<uint16_t *>(topp + RB * 1 + 2 * j) = (uint16_t)prmt(Q[1], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 0 + 2 * j) = (uint16_t)prmt(Q[2], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 3 + 2 * j) = (uint16_t)prmt(Q[5], 0, 0x4420);
                 *reinterpret_cast<uint16_t *>(T + RB * 4 + 2 * j) = (uint16_t)prmt(Q[6], 0, 0x4420);
             } else {
-                dbf_luma_dir(Q, (bsw >> 4) & 0x0f0f0f0fu, dh);
+                dbf_luma_edge0(Q, (bsw >> 4) & 0x0f0f0f0fu, dh);
+                dbf_luma_inner(Q, (bsw >> 4) & 0x0f0f0f0fu, dh);
 #pragma unroll
                 for (int k = 1; k < NQ - 1; k++) {
                     uint8_t *dst = k < TR ? topp + RB * k + 2 * j : T + RB * (k - TR) + 2 * j;
