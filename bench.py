@@ -192,7 +192,7 @@ def cpu_reference(args, frames_per_core, cores):
 
 def auto_cpu_frames(size):
     # ~17 pictures/s/core at 1080p for the reference: aim at 10-20 s per core
-    return {"1080p": 120, "4k": 30, "cif": 2000}[size]
+    return {"1080p": 400, "4k": 100, "cif": 6000}[size]
 
 
 def run_reference(args, rank, world):
