@@ -5,24 +5,30 @@
 // edges then horizontal edges per macroblock; MB(x,y) therefore depends on MB(x-1,y) (whole MB)
 // and on MB(x+1,y-1) (its left-edge filter rewrites columns 13..15 of MB(x,y-1), which MB(x,y)'s
 // top-edge filter reads).  A picture-wide "all vertical, then all horizontal" pass is NOT
-// bit-exact, so the kernel keeps the reference order as a two-macroblock-lag row wavefront.
+// bit-exact, so the kernel keeps the reference order as a row wavefront with a one-macroblock lag.
 //
-// Work decomposition (v3; v2 spent 40 % of its issue slots spinning on shared-memory flags and most of
-// the rest on one-sample-per-register arithmetic and byte shuffling):
+// Work decomposition (v4):
 //  * TWO sample lines per register: every tap (p3..q3) is held as s16x2, the filters are the packed
 //    forms in swar.cuh (VABSDIFF4 / VIADD.16 / VIMNMX.S16x2 / VIADDMNMX.RELU), so one thread filters
 //    two rows (vertical edges) or two columns (horizontal edges) per instruction stream;
 //  * a warp owns one macroblock row of FOUR lanes (streams): 8 threads per stream, always in the
 //    same code path.  Luma and chroma are independent given the boundary strengths and run as
-//    separate warps (role = CTA) with separate progress flags;
-//  * a CTA owns kDbfRows consecutive macroblock rows and runs them in LOCKSTEP: two __syncthreads per
-//    macroblock step (vertical edges | horizontal edges), warp w works on macroblock (step - w): a
-//    ONE-macroblock lag between rows.  Waiting warps sit in the barrier instead of polling.  The four sample rows that cross a row boundary are handed down through a
-//    small shared-memory ring; only every kDbfRows-th row boundary goes through global memory
-//    (progress word + acquire/release), handled by a ninth "I/O" warp so that no filtering warp ever
-//    executes a fence or polls;
-//  * vertical edges are filtered in registers straight from two 16-byte row loads; the transpose for
-//    the horizontal edges is a shared-memory tile written as rows and read as 16-bit column pairs;
+//    separate CTAs (roles) with separate progress words; a CTA draws its role from its arrival order on
+//    its SM so that every SM runs one luma and one chroma CTA;
+//  * a CTA owns kDbfRows consecutive macroblock rows.  Each row warp runs at its own pace; the only
+//    cross-warp dependency -- the top edge of macroblock x needs the last rows of macroblock x of the
+//    row above after the left edge of ITS macroblock x+1 -- goes through a shared-memory ring of
+//    kDbfRing slots guarded by full/empty mbarriers (one arriving lane, hardware-suspended try_wait:
+//    no polling, no CTA-wide barrier).  The left macroblock edge is filtered first and the finished
+//    macroblock handed down before the inner edges, which halves the row-to-row lag of the wavefront;
+//  * only every kDbfRows-th row boundary goes through global memory (progress word per row, role and
+//    stream quad).  Two helper warps own those words: the "in" warp polls the row group above (relaxed
+//    loads, one fence per hand-over -- an acquire load per spin would flush the SM's L1 each time) and
+//    keeps ring[0] up to kDbfRing macroblocks ahead; the "out" thread publishes the CTA's last row.
+//    No filtering warp ever executes a fence or polls;
+//  * vertical edges are filtered in registers straight from two 16-byte row loads (prefetched one
+//    macroblock ahead, the next 128-byte line pulled into L2); the transpose for the horizontal edges
+//    is a private shared-memory tile written as rows and read as 16-bit column pairs;
 //  * all global traffic is full 16-byte (luma) / 8-byte (chroma) rows: a macroblock's rows are stored
 //    once, after the next macroblock's left edge has finalised their last three columns.
 #pragma once
