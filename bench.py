@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=64, help="independent streams per GPU per launch")
     ap.add_argument("--staged", type=int, default=4, help="distinct pre-staged pictures per lane (cycled)")
     ap.add_argument("--refs", type=int, default=1)
+    ap.add_argument("--intra-pct", type=int, default=0, help="side workload: %% of intra macroblocks inside the P pictures (0 = the headline workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-parts", default="hcd", help="debug: which legs the e2e step runs (h = H2D, c = compute, d = D2H)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -57,7 +58,7 @@ def parse_args():
 
 
 def synth_kwargs(args, lane, rank):
-    return dict(n_refs=args.refs, seed=stream_seed(rank, lane), first_intra=0, confine_mv=1, intra_pct=0,
+    return dict(n_refs=args.refs, seed=stream_seed(rank, lane), first_intra=0, confine_mv=1, intra_pct=args.intra_pct,
                 coded_pct=25, max_level=8, mv_range=16, sub8x8=1, skip_pct=5, qp_min=20, qp_max=40, qp_step=2)
 
 
@@ -246,7 +247,7 @@ def workload_config(args, lanes):
     return {
         "workload": f"BASELINE.json configs[2]: synthetic {args.size} P-frame streams ({16*mb_w}x{16*mb_h} coded), "
                     f"random qpel MVs over all partition shapes incl. sub-8x8, 25% coded 4x4 blocks, slice QP sweep 20..40, "
-                    f"deblocking on, {args.refs} reference frame(s)",
+                    f"deblocking on, {args.refs} reference frame(s)" + (f", {args.intra_pct}% intra macroblocks" if args.intra_pct else ""),
         "lanes_per_gpu": lanes, "staged_pictures_per_lane": args.staged, "mb_per_picture": mb_w * mb_h,
         "l2_policy": "inputs larger than L2: every step streams lanes x (syntax + reference + output picture) >> 126 MB",
         "parallelism": "independent streams (replicas), no collective",

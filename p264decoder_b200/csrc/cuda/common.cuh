@@ -26,9 +26,9 @@ struct FrameDesc {
     const int16_t *coefs;
     uint8_t *cur[3];                    // plane origins (sample 0,0) of the picture being reconstructed
     const uint8_t *ref[kMaxRefs][3];    // list-0 reference plane origins
-    int *row_progress;                  // [3][mb_h]: intra, luma deblock, chroma deblock wavefronts
+    int *row_progress;                  // [3][mb_h]: (unused), luma deblock, chroma deblock wavefronts
     struct DeblockSide *dbf_bs;         // per-MB boundary strengths (deblock_bs_kernel -> deblock_kernel)
-    uint32_t *dbf_qp;                   // per-MB qp | qp_left << 8 | qp_top << 16
+    int *intra_work;                    // [1 + 2*n_mb]: run count, run starts, per-MB done epochs (recon_intra.cuh)
     int slice_type, deblock, alpha_off, beta_off, chroma_qp_off, n_intra, num_ref, pad_;
 };
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #define P264B200_DEFINE_KERNELS 1
@@ -63,7 +64,9 @@ struct p264b200_engine {
     size_t out_bytes = 0;
     PackSrc *d_pack = nullptr;     // [lanes][n_slots] plane origins
     DeblockSide *d_bs = nullptr;   // [lanes][n_mb]
-    uint32_t *d_dqp = nullptr;     // [lanes][n_mb]
+    int *d_intra = nullptr;        // [lanes][1 + 2*n_mb]: intra runs + per-MB done epochs
+    int intra_epoch = 0;
+    std::vector<int> slot_nintra;  // [step][lane]: intra macroblocks of the staged picture
     int *d_sync = nullptr;  // [groups][kSyncHdr] tickets + per-SM arrival counters, then [lanes][3*mb_h]: intra, luma deblock, chroma deblock wavefronts
     size_t sync_bytes = 0;
     std::vector<uint8_t> slot_flags;  // [step][lane]: bit0 intra MBs present, bit1 deblock on, bit2 P slice
@@ -196,7 +199,7 @@ void p264b200_engine_destroy(p264b200_engine *e)
     cudaFree(e->d_bs);
     cudaFree(e->d_out);
     cudaFree(e->d_pack);
-    cudaFree(e->d_dqp);
+    cudaFree(e->d_intra);
     if (e->h_descs) cudaFreeHost(e->h_descs);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->s_h2d) cudaStreamSynchronize(e->s_h2d);
@@ -273,7 +276,9 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaMallocHost(&e->h_descs, slots * sizeof(FrameDesc))) != cudaSuccess) fail("cudaMallocHost descs", err);
     if (!rc && (err = cudaMalloc(&e->d_sync, e->sync_bytes)) != cudaSuccess) fail("cudaMalloc sync", err);
     if (!rc && (err = cudaMalloc(&e->d_bs, (size_t)cfg->lanes * n_mb * sizeof(DeblockSide))) != cudaSuccess) fail("cudaMalloc bs", err);
-    if (!rc && (err = cudaMalloc(&e->d_dqp, (size_t)cfg->lanes * n_mb * sizeof(uint32_t))) != cudaSuccess) fail("cudaMalloc dqp", err);
+    if (!rc && (err = cudaMalloc(&e->d_intra, (size_t)cfg->lanes * (1 + 2 * n_mb) * sizeof(int))) != cudaSuccess) fail("cudaMalloc intra work", err);
+    if (!rc && (err = cudaMemset(e->d_intra, 0, (size_t)cfg->lanes * (1 + 2 * n_mb) * sizeof(int))) != cudaSuccess) fail("memset intra work", err);
+    e->slot_nintra.assign(slots, 0);
     if (!rc && (err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
     if (!rc && (err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_compute, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
@@ -348,7 +353,7 @@ int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_sy
         for (int c = 0; c < 3; c++) d.ref[i][c] = e->plane(lane, h.ref_slot[i], c);
     d.row_progress = e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)lane * 3 * g.mb_h;
     d.dbf_bs = e->d_bs + (size_t)lane * n_mb;
-    d.dbf_qp = e->d_dqp + (size_t)lane * n_mb;
+    d.intra_work = e->d_intra + (size_t)lane * (1 + 2 * n_mb);
     d.slice_type = h.slice_type;
     d.deblock = h.deblock;
     d.alpha_off = h.alpha_c0_offset;
@@ -356,6 +361,7 @@ int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_sy
     d.chroma_qp_off = h.chroma_qp_index_offset;
     d.n_intra = h.n_intra;
     d.num_ref = h.num_ref;
+    e->slot_nintra[s] = h.n_intra;
     e->slot_flags[s] = (uint8_t)((h.n_intra > 0) | ((h.deblock != 0) << 1) | ((h.slice_type == P264B200_SLICE_P) << 2));
     if (lane == 0) e->step_dst_mask[step] = 0;
     e->step_dst_mask[step] |= 1u << h.dst_slot;
@@ -471,7 +477,10 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (intra) {
             ProfScope p(e, K_INTRA, st);
-            recon_intra_kernel<<<g.mb_h * nl, 32, 0, st>>>(descs, g, tickets + 0);
+            int max_intra = 0;
+            for (int l = l0; l < l1; l++) max_intra = std::max(max_intra, e->slot_nintra[(size_t)step * e->cfg.lanes + l]);
+            intra_runs_kernel<<<nl, kRunThreads, 0, st>>>(descs, g);
+            recon_intra_kernel<<<(unsigned)std::min<long long>((long long)max_intra, n_mb) * nl, 32, 0, st>>>(descs, g, nl, tickets + 0, ++e->intra_epoch);
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);

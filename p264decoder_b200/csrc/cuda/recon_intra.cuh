@@ -4,12 +4,17 @@
 // valid_intra16x16/4x4/8x8c_mode (decoder/macroblock.c:635-753), the predictors of
 // core/predict.c:55-638 and the neighbour flags of core/macroblock.c:1210-1231.
 //
-// One warp owns one macroblock row of one lane.  Row y may reconstruct MB x once row y-1 has
-// published progress >= min(x+2, mb_w) (left / top-left / top / top-right neighbours are
-// pre-deblock samples of the same picture).  Inter MBs were written by recon_inter before this
-// kernel starts, so a row only ever waits in front of an intra MB.  Rows are handed out by an
-// atomic ticket in dependency order, which makes the spin-wait deadlock-free whatever order
-// the hardware schedules CTAs in.
+// Work item = a RUN of horizontally adjacent intra macroblocks, walked left to right by one warp (the left
+// neighbour is then the warp's own previous macroblock).  Inter macroblocks were written by recon_inter before
+// this kernel starts, so a macroblock only has to wait for those of its top-left / top / top-right neighbours
+// that are intra themselves: per-macroblock "done" words (value = the launch's epoch, so nothing is ever
+// cleared), polled with relaxed loads + one fence.  An I picture degenerates to the classic row wavefront
+// (run = row, every macroblock waits for the row above to be two macroblocks ahead); the few intra
+// macroblocks of a P picture have almost no intra neighbours and reconstruct in parallel instead of
+// queueing behind a row-serial progress counter (5 % intra macroblocks: 5.9 ms -> see profiles/README.md).
+// Runs are listed in raster order by intra_runs_kernel and handed out by an atomic ticket, run-index-major
+// over the lanes: every dependency of a run has a smaller ticket, which makes the spin-wait deadlock-free
+// whatever order the hardware schedules CTAs in.
 #pragma once
 #include "common.cuh"
 
@@ -305,7 +310,53 @@ static __device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const G
 }
 
 #ifdef P264B200_DEFINE_KERNELS
-__global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__restrict__ descs, Geometry g, int *ticket)
+// Per lane: work[0] = number of runs, work[1 + i] = first macroblock of run i (raster order),
+// work[1 + n_mb + mb] = epoch of the launch that last reconstructed intra macroblock mb.
+constexpr int kRunThreads = 1024;
+__global__ void __launch_bounds__(kRunThreads) intra_runs_kernel(const FrameDesc *__restrict__ descs, Geometry g)
+{
+    __shared__ int warp_sum[kRunThreads / 32];
+    const FrameDesc &fd = descs[blockIdx.x];
+    int *work = fd.intra_work;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (fd.n_intra == 0) {
+        if (tid == 0) work[0] = 0;
+        return;
+    }
+    const int n_mb = g.mb_w * g.mb_h;
+    const int per = (n_mb + kRunThreads - 1) / kRunThreads, m0 = tid * per, m1 = min(n_mb, m0 + per);
+    auto starts_run = [&](int mb) {
+        if (!P264B200_IS_INTRA(__ldg(&fd.mbs[mb].mb_type))) return false;
+        return mb % g.mb_w == 0 || !P264B200_IS_INTRA(__ldg(&fd.mbs[mb - 1].mb_type));
+    };
+    int cnt = 0;
+    for (int mb = m0; mb < m1; mb++) cnt += starts_run(mb);
+    // exclusive scan of cnt over the block
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        warp_sum[lane] = v;
+    }
+    __syncthreads();
+    int pos = incl - cnt + (wid ? warp_sum[wid - 1] : 0);
+    for (int mb = m0; mb < m1; mb++)
+        if (starts_run(mb)) work[1 + pos++] = mb;
+    if (tid == kRunThreads - 1) work[0] = pos;
+}
+
+__global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int epoch)
 {
     __shared__ IntraSmem s;
     __shared__ int s_ticket;
@@ -313,38 +364,38 @@ __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__rest
     if (lane == 0) s_ticket = atomicAdd(ticket, 1);
     __syncwarp();
     const int t = s_ticket;
-    const int lane_id = t / g.mb_h, row = t % g.mb_h;
-    const FrameDesc &fd = descs[lane_id];
-    if (fd.n_intra == 0) return;
-    int *prog = fd.row_progress;  // [0 .. mb_h) intra wavefront
-    const p264b200_mb *mbs = fd.mbs + (size_t)row * g.mb_w;
+    const int run = t / n_lanes;
+    const FrameDesc &fd = descs[t - run * n_lanes];
+    const int n_mb = g.mb_w * g.mb_h;
+    const int *work = fd.intra_work;
+    if (run >= work[0]) return;
+    int *done = fd.intra_work + 1 + n_mb;
+    const int mb0 = work[1 + run], row = mb0 / g.mb_w;
+    const p264b200_mb *mbs = fd.mbs;
 
-    for (int base = 0; base < g.mb_w; base += 32) {
-        const int x = base + lane;
-        const bool intra = x < g.mb_w && P264B200_IS_INTRA(mbs[x].mb_type);
-        unsigned mask = __ballot_sync(0xffffffffu, intra);
-        while (mask) {
-            const int mbx = base + __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (row > 0) {
-                const int need = min(mbx + 2, g.mb_w);
-                if (lane == 0) {
-                    unsigned ns = 64;
-                    while (ld_acquire(prog + row - 1) < need) {
+    for (int mb = mb0, mbx = mb0 - row * g.mb_w; mbx < g.mb_w && P264B200_IS_INTRA(mbs[mb].mb_type); mb++, mbx++) {
+        if (row > 0) {
+            // lanes 0..2: top-left, top, top-right; only intra neighbours are reconstructed by this kernel
+            const int nx = mbx - 1 + lane;
+            bool waited = false;
+            if (lane < 3 && nx >= 0 && nx < g.mb_w) {
+                const int nb = mb - g.mb_w - 1 + lane;
+                if (P264B200_IS_INTRA(mbs[nb].mb_type)) {
+                    unsigned ns = 32;
+                    while (ld_relaxed(done + nb) != epoch) {
                         __nanosleep(ns);
-                        if (ns < 4096) ns <<= 1;
+                        if (ns < 512) ns <<= 1;
                     }
+                    waited = true;
                 }
-                __syncwarp();
             }
-            recon_intra_mb(s, fd, g, mbs[mbx], mbx, row, lane);
-            __threadfence();
+            if (waited) asm volatile("fence.acq_rel.gpu;" ::: "memory");
             __syncwarp();
-            if (lane == 0) st_release(prog + row, mbx + 1);
         }
+        recon_intra_mb(s, fd, g, mbs[mb], mbx, row, lane);
+        __syncwarp();
+        if (lane == 0) st_release(done + mb, epoch);  // release.gpu, cumulative over the other lanes' stores (__syncwarp)
     }
-    __syncwarp();
-    if (lane == 0) st_release(prog + row, g.mb_w);
 }
 
 #endif  // P264B200_DEFINE_KERNELS

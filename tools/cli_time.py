@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""Wall time of the two command-line decoders on bin/f26.264 (BASELINE.json configs[0] / [1]): the reference's own
+CLI built in oracle/_ref and tools/p264dec_b200.c on the drop-in library.  Needs a GPU for the second."""
+import hashlib
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "_ref"
+src = REF / "f26.264"
+
+
+def run(exe, out, n=3):
+    best = None
+    for _ in range(n):
+        t0 = time.perf_counter()
+        r = subprocess.run([str(exe), "-d", str(src), out], capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode:
+            sys.exit(f"{exe} failed: {r.stderr[-400:]}")
+        best = dt if best is None else min(best, dt)
+    return best, hashlib.md5(Path(out).read_bytes()).hexdigest()
+
+
+t_ref, m_ref = run(REF / "p264dec_ref", "/tmp/f26_ref.yuv")
+t_gpu, m_gpu = run(ROOT / "p264decoder_b200" / "lib" / "p264dec_b200", "/tmp/f26_b200.yuv")
+print(f"reference CLI : {t_ref:.3f} s  ({300 / t_ref:.0f} CIF frames/s)  md5 {m_ref}")
+print(f"B200 CLI      : {t_gpu:.3f} s  ({300 / t_gpu:.0f} CIF frames/s, incl. process start + CUDA context)  md5 {m_gpu}")
+print("byte-identical" if m_ref == m_gpu else "DIFFERENT")
