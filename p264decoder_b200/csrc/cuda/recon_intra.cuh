@@ -24,7 +24,8 @@ constexpr int kIntraWarpsPerCta = 1;
 constexpr int kTS = 24;  // luma tile row stride: rows -1..15, cols -1..19
 constexpr int kCS = 12;  // chroma tile row stride: rows -1..7, cols -1..7
 
-struct IntraSmem {
+struct __align__(16) IntraSmem {
+    p264b200_mb mb;     // the macroblock record (every field is read many times, across warp barriers)
     uint8_t y[17 * kTS];
     uint8_t c[2][9 * kCS];
     short res_y[16][16];
@@ -106,7 +107,15 @@ __device__ __forceinline__ void plane_params(const uint8_t *tile, int ts, int &i
     }
 }
 
-static __device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const Geometry &g, const p264b200_mb &m, int mbx,
+// what recon_intra_mb needs of the FrameDesc, held in registers (the descriptor lives in global memory and would
+// be re-read after every warp barrier)
+struct IntraCtx {
+    uint8_t *cur[3];
+    const int16_t *coefs;
+    int chroma_qp_off;
+};
+
+static __device__ void recon_intra_mb(IntraSmem &s, const IntraCtx &fd, const Geometry &g, const p264b200_mb &m, int mbx,
                                int mby, int lane)
 {
     const bool has_left = mbx > 0, has_top = mby > 0;
@@ -118,20 +127,25 @@ static __device__ void recon_intra_mb(IntraSmem &s, const FrameDesc &fd, const G
     const int qpc = c_chroma_qp[clip3i(qp + fd.chroma_qp_off, 0, 51)];
     const bool i16 = m.mb_type == P264B200_MB_I16x16;
 
-    // ---- neighbours into the tiles (L2 loads: written by other SMs in this or the previous kernel)
-    if (lane < 21) {
-        const int c = lane - 1;
-        const bool ok = has_top && (c >= 0 || has_tl) && (c < 16 || has_tr);
-        TY(s, -1, c) = ok ? __ldcg(gy - g.y_stride + c) : 128;
-    }
-    if (lane < 16) TY(s, lane, -1) = has_left ? __ldcg(gy + lane * g.y_stride - 1) : 128;
-    if (lane < 18) {
-        const int p = lane / 9, c = lane % 9 - 1;
-        TC(s, p, -1, c) = (has_top && (c >= 0 || has_tl)) ? __ldcg(gc[p] - g.c_stride + c) : 128;
-    }
-    if (lane < 16) {
-        const int p = lane >> 3, r = lane & 7;
-        TC(s, p, r, -1) = has_left ? __ldcg(gc[p] + r * g.c_stride - 1) : 128;
+    // ---- neighbours into the tiles (L2 loads: written by other SMs in this or the previous kernel); all four
+    // loads are issued before the first store so that their latencies overlap
+    {
+        const int c0 = lane - 1;
+        const bool ok0 = lane < 21 && has_top && (c0 >= 0 || has_tl) && (c0 < 16 || has_tr);
+        const bool ok1 = lane < 16 && has_left;
+        const int p2 = lane / 9, c2 = lane % 9 - 1;
+        const bool ok2 = lane < 18 && has_top && (c2 >= 0 || has_tl);
+        const int p3 = (lane >> 3) & 1, r3 = lane & 7;
+        const bool ok3 = lane < 16 && has_left;
+        uint8_t v0 = 128, v1 = 128, v2 = 128, v3 = 128;
+        if (ok0) v0 = __ldcg(gy - g.y_stride + c0);
+        if (ok1) v1 = __ldcg(gy + lane * g.y_stride - 1);
+        if (ok2) v2 = __ldcg(gc[p2] - g.c_stride + c2);
+        if (ok3) v3 = __ldcg(gc[p3] + r3 * g.c_stride - 1);
+        if (lane < 21) TY(s, -1, c0) = v0;
+        if (lane < 16) TY(s, lane, -1) = v1;
+        if (lane < 18) TC(s, p2, -1, c2) = v2;
+        if (lane < 16) TC(s, p3, r3, -1) = v3;
     }
 
     // ---- residual samples of all 24 blocks, independent of the prediction
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(kRunThreads) intra_runs_kernel(const FrameDesc
     if (tid == kRunThreads - 1) work[0] = pos;
 }
 
-__global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int epoch)
+__global__ void __launch_bounds__(32, 32) recon_intra_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *ticket, int epoch)
 {
     __shared__ IntraSmem s;
     __shared__ int s_ticket;
@@ -372,6 +386,10 @@ __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__rest
     int *done = fd.intra_work + 1 + n_mb;
     const int mb0 = work[1 + run], row = mb0 / g.mb_w;
     const p264b200_mb *mbs = fd.mbs;
+    IntraCtx ctx;
+    ctx.cur[0] = fd.cur[0], ctx.cur[1] = fd.cur[1], ctx.cur[2] = fd.cur[2];
+    ctx.coefs = fd.coefs;
+    ctx.chroma_qp_off = fd.chroma_qp_off;
 
     for (int mb = mb0, mbx = mb0 - row * g.mb_w; mbx < g.mb_w && P264B200_IS_INTRA(mbs[mb].mb_type); mb++, mbx++) {
         if (row > 0) {
@@ -392,7 +410,9 @@ __global__ void __launch_bounds__(32) recon_intra_kernel(const FrameDesc *__rest
             if (waited) asm volatile("fence.acq_rel.gpu;" ::: "memory");
             __syncwarp();
         }
-        recon_intra_mb(s, fd, g, mbs[mb], mbx, row, lane);
+        if (lane < 6) reinterpret_cast<uint4 *>(&s.mb)[lane] = __ldg(reinterpret_cast<const uint4 *>(mbs + mb) + lane);
+        __syncwarp();
+        recon_intra_mb(s, ctx, g, s.mb, mbx, row, lane);
         __syncwarp();
         if (lane == 0) st_release(done + mb, epoch);  // release.gpu, cumulative over the other lanes' stores (__syncwarp)
     }
