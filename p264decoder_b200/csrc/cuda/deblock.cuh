@@ -602,8 +602,8 @@ __device__ __forceinline__ void deblock_out_thread(DbfSmem &sm, const FrameDesc 
 // grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups.  A CTA draws its work at run time:
 //  * the role from its arrival order on its SM (first luma, second chroma, ...), so that co-resident CTAs are
 //    one luma + one chroma -- luma is the heavier role, and two luma CTAs on one SM would pace every chain below them;
-//  * (quad, row group) from a per-role ticket in dependency order (the group above of the same quad and role
-//    always has a smaller ticket, i.e. is resident or finished).  A role whose tickets are used up falls back to the other.
+//  * (row group, quad) from a per-role ticket, row-group-major: the group above of the same quad and role always
+//    has a smaller ticket, i.e. is resident or finished.  A role whose tickets are used up falls back to the other.
 // sync: [0] intra ticket (other kernel), [1] luma ticket, [2] chroma ticket, [4 + smid] arrivals per SM
 __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *sync, int trace_ticket)
 {
@@ -630,7 +630,10 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
     __syncthreads();
     const int tk = sm.ticket;
     const int role = tk & 1, u = tk >> 1;
-    const int quad = u / groups, grp = u % groups;
+    // row-group-major over the stream quads: when there are more CTAs than fit on the machine, the resident ones are
+    // the upper row groups of EVERY quad (all busy) rather than whole chains of a few quads (lower groups idle)
+    const int quads = (int)(gridDim.x >> 1) / groups;
+    const int grp = u / quads, quad = u - grp * quads;
     const bool trace = tk == trace_ticket;
     const bool times = trace_ticket >= 0 && tk < 2048 && threadIdx.x == 0;
     if (times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
