@@ -303,11 +303,15 @@ __device__ __forceinline__ void mc_chroma_4x4(const uint8_t *__restrict__ src, i
     }
 }
 
+constexpr int kYPitch = 16 * kTileW + 8, kCPitch = 8 * kTileW + 8;
+
 #ifdef P264B200_DEFINE_KERNELS
 struct InterSmem {
     p264b200_mb mb[kTileMbs];                       // the tile's macroblock records
-    uint8_t y[16 * kTileH][16 * kTileW];            // picture tile, luma
-    uint8_t c[2][8 * kTileH][8 * kTileW];           // picture tile, Cb / Cr
+    // picture tile.  Rows are padded by 8 bytes: with a pitch of exactly 32 (16) banks every row of a 4x4 block falls
+    // into the same bank, so the 16 blocks of one macroblock were a 4-way conflict on every tile access
+    uint8_t y[16 * kTileH][kYPitch];                // luma
+    uint8_t c[2][8 * kTileH][kCPitch];              // Cb / Cr
     uint16_t perm[16 * kTileMbs];                   // luma blocks bucketed by class: block | class << 12
     uint16_t cperm[8 * kTileMbs];                   // chroma blocks: one-MV quadrants from the front, per-cell MVs from the back
     uint16_t res[24 * kTileMbs];                    // residual work: full blocks (luma: block, chroma: 512 + block) from the
@@ -466,13 +470,13 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
         if (!chroma) {
             const int b = q & 15;
             t = &sm.y[16 * tmy + 4 * (b >> 2)][16 * tmx + 4 * (b & 3)];
-            pitch = 16 * kTileW;
+            pitch = kYPitch;
             qp = m.qp;
             lvl = fd.coefs + m.coef_off + 16 * __popc(m.luma_mask & ((1u << b) - 1));
         } else {
             const int cb = q & 7, plane = cb >> 2, i = cb & 3;
             t = &sm.c[plane][8 * tmy + 4 * (i >> 1)][8 * tmx + 4 * (i & 1)];
-            pitch = 8 * kTileW;
+            pitch = kCPitch;
             qp = c_chroma_qp[clip3i(m.qp + fd.chroma_qp_off, 0, 51)];
             const int16_t *cf = fd.coefs + m.coef_off + 16 * __popc(m.luma_mask);
             int dc[4];
@@ -500,8 +504,8 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
         const int r0 = ((i == 0 ? dc[0] : i == 1 ? dc[1] : i == 2 ? dc[2] : dc[3]) + 32) >> 6;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const uint32_t p = *reinterpret_cast<const uint32_t *>(t + r * 8 * kTileW);
-            *reinterpret_cast<uint32_t *>(t + r * 8 * kTileW) =
+            const uint32_t p = *reinterpret_cast<const uint32_t *>(t + r * kCPitch);
+            *reinterpret_cast<uint32_t *>(t + r * kCPitch) =
                 pack4_sat_u8((int)(p & 0xff) + r0, (int)((p >> 8) & 0xff) + r0, (int)((p >> 16) & 0xff) + r0, (int)(p >> 24) + r0);
         }
     }
@@ -513,8 +517,10 @@ __global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const Fra
         const int i = tid + kInterThreads * rd, row = i >> 3, seg = i & 7;  // 64 rows x 8 macroblock-wide segments
         const int mb = (row >> 4) * kTileW + seg;
         if (!P264B200_IS_INTRA(sm.mb[mb].mb_type))
-            *reinterpret_cast<uint4 *>(fd.cur[0] + (ptrdiff_t)(16 * mby0 + row) * g.y_stride + 16 * (mbx0 + seg)) =
-                *reinterpret_cast<const uint4 *>(&sm.y[row][16 * seg]);
+        {
+            const uint2 a = *reinterpret_cast<const uint2 *>(&sm.y[row][16 * seg]), b = *reinterpret_cast<const uint2 *>(&sm.y[row][16 * seg + 8]);
+            *reinterpret_cast<uint4 *>(fd.cur[0] + (ptrdiff_t)(16 * mby0 + row) * g.y_stride + 16 * (mbx0 + seg)) = make_uint4(a.x, a.y, b.x, b.y);
+        }
     }
 #pragma unroll
     for (int plane = 0; plane < 2; plane++) {
