@@ -70,6 +70,12 @@ def test_lanes_batched():
     _run_stream(9, 7, 5, lanes=5, n_refs=2, seed=11, intra_pct=8)
 
 
+def test_tall_picture_many_lanes_dense_intra():
+    # 19 macroblock rows = three deblock row groups (8 + 8 + 3), 9 lanes = two full stream quads + one lane,
+    # 40 % intra macroblocks = long intra runs with intra neighbours above (the per-macroblock wait path)
+    _run_stream(7, 19, 3, lanes=9, n_refs=1, seed=19, intra_pct=40, sweep_offsets=1)
+
+
 def test_1080p_stream():
     _run_stream(120, 68, 3, n_refs=1, seed=264, intra_pct=2)
 
