@@ -138,33 +138,106 @@ __device__ __forceinline__ uint32_t pack_edge_params(int qp, int alpha_off, int 
 
 #ifdef P264B200_DEFINE_KERNELS
 
-// one thread per (macroblock, segment): 8 boundary strengths -> one word; thread seg 0 also writes the QP word
-__global__ void __launch_bounds__(256) deblock_bs_kernel(const FrameDesc *__restrict__ descs, Geometry g)
+// bS of one 4-sample segment from values already in registers (same rule as boundary_strength above)
+__device__ __forceinline__ int bs_of(bool intra_any, int strong, unsigned coded, int rq, int rp, int vq, int vp)
+{
+    if (intra_any) return strong;
+    if (coded & 1u) return 2;
+    const int dx = abs((int)(short)(vq & 0xffff) - (int)(short)(vp & 0xffff)), dy = abs((vq >> 16) - (vp >> 16));
+    return (rq != rp || dx >= 4 || dy >= 4) ? 1 : 0;
+}
+
+// One thread per macroblock: its record (five 16-byte loads) plus the last column / row of the left / top
+// neighbour give all 32 boundary strengths and the six edge-parameter words; three 16-byte stores.
+__global__ void __launch_bounds__(128) deblock_bs_kernel(const FrameDesc *__restrict__ descs, Geometry g)
 {
     const FrameDesc &fd = descs[blockIdx.y];
     if (!fd.deblock) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mb_xy = t >> 2, seg = t & 3;
+    const int mb_xy = blockIdx.x * blockDim.x + threadIdx.x;
     if (mb_xy >= g.mb_w * g.mb_h) return;
-    const int mbx = mb_xy % g.mb_w, mby = mb_xy / g.mb_w;
-    const p264b200_mb *m = fd.mbs + mb_xy;
-    uint32_t w = 0;
+    const int mby = mb_xy / g.mb_w, mbx = mb_xy - mby * g.mb_w;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(fd.mbs + mb_xy);
+    int mv[16];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        int bv = 0, bh = 0;
-        if (e > 0 || mbx > 0) bv = boundary_strength(m, e > 0 ? m : m - 1, 0, e, seg);
-        if (e > 0 || mby > 0) bh = boundary_strength(m, e > 0 ? m : m - g.mb_w, 1, e, seg);
-        w |= (uint32_t)(bv | (bh << 4)) << (8 * e);
+    for (int i = 0; i < 4; i++) {
+        const uint4 q = __ldg(rec + i);
+        mv[4 * i] = (int)q.x, mv[4 * i + 1] = (int)q.y, mv[4 * i + 2] = (int)q.z, mv[4 * i + 3] = (int)q.w;
     }
-    fd.dbf_bs[mb_xy].bs[seg] = w;
-    if (seg < 3) {
-        // seg 0/1/2 -> left / top / inner edge parameters, luma QP average and mapped chroma QP average
-        const int qp = m->qp_dbf, qn = seg == 0 ? (mbx > 0 ? m[-1].qp_dbf : qp) : seg == 1 ? (mby > 0 ? m[-g.mb_w].qp_dbf : qp) : qp;
-        const int off = fd.chroma_qp_off;
-        const int qc = c_chroma_qp[clip3i(qp + off, 0, 51)], qcn = c_chroma_qp[clip3i(qn + off, 0, 51)];
-        fd.dbf_bs[mb_xy].luma[seg] = pack_edge_params((qp + qn + 1) >> 1, fd.alpha_off, fd.beta_off);
-        fd.dbf_bs[mb_xy].chroma[seg] = pack_edge_params((qc + qcn + 1) >> 1, fd.alpha_off, fd.beta_off);
+    const uint4 h = __ldg(rec + 4);  // ref[4] | mb_type qp qp_dbf cbp | luma_mask ...
+    const int type = h.y & 0xff, qp = (h.y >> 16) & 0xff;
+    const unsigned mask = h.z & 0xffff;
+    const bool intra = P264B200_IS_INTRA(type);
+    int ref[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) ref[i] = (int)(signed char)(h.x >> (8 * i));
+
+    // left neighbour: blocks 3, 7, 11, 15 and 8x8 quadrants 1, 3; top neighbour: blocks 12..15, quadrants 2, 3
+    int lmv[4] = {0, 0, 0, 0}, tmv[4] = {0, 0, 0, 0}, lref[2] = {0, 0}, tref[2] = {0, 0}, lqp = qp, tqp = qp;
+    unsigned lmask = 0, tmask = 0;
+    bool lintra = false, tintra = false;
+    if (mbx > 0) {
+        const uint4 *nr = rec - 6;
+#pragma unroll
+        for (int i = 0; i < 4; i++) lmv[i] = (int)__ldg(reinterpret_cast<const uint32_t *>(nr + i) + 3);
+        const uint4 nh = __ldg(nr + 4);
+        lref[0] = (int)(signed char)(nh.x >> 8), lref[1] = (int)(signed char)(nh.x >> 24);
+        lintra = P264B200_IS_INTRA(nh.y & 0xff);
+        lqp = (nh.y >> 16) & 0xff;
+        lmask = nh.z & 0xffff;
     }
+    if (mby > 0) {
+        const uint4 *nr = rec - 6 * g.mb_w;
+        const uint4 q = __ldg(nr + 3);
+        tmv[0] = (int)q.x, tmv[1] = (int)q.y, tmv[2] = (int)q.z, tmv[3] = (int)q.w;
+        const uint4 nh = __ldg(nr + 4);
+        tref[0] = (int)(signed char)(nh.x >> 16), tref[1] = (int)(signed char)(nh.x >> 24);
+        tintra = P264B200_IS_INTRA(nh.y & 0xff);
+        tqp = (nh.y >> 16) & 0xff;
+        tmask = nh.z & 0xffff;
+    }
+
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int seg = 0; seg < 4; seg++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int bv = 0, bh = 0;
+            {
+                // vertical edge e, rows 4*seg..: q block (e, seg), p block to its left
+                const int bq = 4 * seg + e;
+                if (e > 0)
+                    bv = bs_of(intra, 3, (mask >> bq) | (mask >> (bq - 1)), ref[(bq >> 3) * 2 + ((bq & 3) >> 1)],
+                               ref[((bq - 1) >> 3) * 2 + (((bq - 1) & 3) >> 1)], mv[bq], mv[bq - 1]);
+                else if (mbx > 0)
+                    bv = bs_of(intra || lintra, 4, (mask >> bq) | (lmask >> (bq + 3)), ref[(bq >> 3) * 2], lref[seg >> 1], mv[bq], lmv[seg]);
+            }
+            {
+                // horizontal edge e, columns 4*seg..: q block (seg, e), p block above it
+                const int bq = 4 * e + seg;
+                if (e > 0)
+                    bh = bs_of(intra, 3, (mask >> bq) | (mask >> (bq - 4)), ref[(bq >> 3) * 2 + ((bq & 3) >> 1)],
+                               ref[((bq - 4) >> 3) * 2 + (((bq - 4) & 3) >> 1)], mv[bq], mv[bq - 4]);
+                else if (mby > 0)
+                    bh = bs_of(intra || tintra, 4, (mask >> bq) | (tmask >> (12 + seg)), ref[seg >> 1], tref[seg >> 1], mv[bq], tmv[seg]);
+            }
+            w[seg] |= (uint32_t)(bv | (bh << 4)) << (8 * e);
+        }
+    }
+    // left / top / inner edge parameters: luma QP average and mapped chroma QP average (core/frame.c:476-483,600-601)
+    const int off = fd.chroma_qp_off;
+    const int qc = c_chroma_qp[clip3i(qp + off, 0, 51)];
+    uint32_t pl[3], pc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int qn = k == 0 ? lqp : k == 1 ? tqp : qp;
+        const int qcn = c_chroma_qp[clip3i(qn + off, 0, 51)];
+        pl[k] = pack_edge_params((qp + qn + 1) >> 1, fd.alpha_off, fd.beta_off);
+        pc[k] = pack_edge_params((qc + qcn + 1) >> 1, fd.alpha_off, fd.beta_off);
+    }
+    uint4 *out = reinterpret_cast<uint4 *>(fd.dbf_bs + mb_xy);
+    out[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    out[1] = make_uint4(pl[0], pl[1], pl[2], 0);
+    out[2] = make_uint4(pc[0], pc[1], pc[2], 0);
 }
 
 

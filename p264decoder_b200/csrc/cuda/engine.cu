@@ -442,8 +442,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         CK(join_groups(e));
         CK(cudaMemsetAsync(e->d_sync, 0, e->sync_bytes, e->stream));
     }
-    const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
-                      2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
+    const int words = border_threads(g.width, g.height);
     for (int gi = 0; gi < G; gi++) {
         // lanes [l0, l1) of this group; four lanes share a deblock warp, so groups start on multiples of four
         const int per = ((n_lanes + G - 1) / G + kDbfQuad - 1) & ~(kDbfQuad - 1);
@@ -473,7 +472,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         if (G > 1) CK(cudaEventRecord(e->ev_mc[gi], st));
         if (dbf) {
             ProfScope p(e, K_DEBLOCK_BS, st);
-            deblock_bs_kernel<<<dim3((4 * n_mb + 255) / 256, nl), 256, 0, st>>>(descs, g);
+            deblock_bs_kernel<<<dim3((n_mb + 127) / 128, nl), 128, 0, st>>>(descs, g);
         }
         if (intra) {
             ProfScope p(e, K_INTRA, st);
@@ -521,8 +520,7 @@ int p264b200_frame_upload(p264b200_engine *e, int lane, int slot, const uint8_t 
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 0), g.y_stride, y, y_stride, g.width, g.height, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 1), g.c_stride, u, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpy2DAsync(e->plane(lane, slot, 2), g.c_stride, v, c_stride, g.width / 2, g.height / 2, cudaMemcpyHostToDevice, e->stream));
-    const int words = 2 * kLumaPad * ((g.width + 2 * kLumaPad) >> 2) + g.height * (kLumaPad >> 1) +
-                      2 * (2 * kChromaPad * ((g.width / 2 + 2 * kChromaPad) >> 2) + (g.height / 2) * (kChromaPad >> 1));
+    const int words = border_threads(g.width, g.height);
     e->launches++;
     border_kernel<<<dim3((words + 255) / 256, 1), 256, 0, e->stream>>>(nullptr, g, e->plane(lane, slot, 0), e->plane(lane, slot, 1),
                                                                       e->plane(lane, slot, 2));
