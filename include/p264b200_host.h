@@ -45,6 +45,33 @@ int p264b200_nal_unescape(const uint8_t *src, int size, uint8_t *dst, int *nal_t
 int p264b200_cavlc_table_entry(int kind, int table, int sym, int *len, int *bits);
 
 /* ------------------------------------------------------------------------- *
+ * Multi-stream decoder: N independent Annex-B byte streams of the
+ * same coded size, one engine lane each.  Per step every stream parses up to its next complete
+ * picture on a pool of host threads (what decoder/decoder.c:598-622 does for one stream), then ONE
+ * batched stage + reconstruction + download serves all lanes.  The reference has no counterpart:
+ * its CLI (p264decoder.c:164-381) decodes one stream on one core.  Needs a CUDA device.
+ * ------------------------------------------------------------------------- */
+typedef struct p264b200_multi p264b200_multi;
+typedef struct p264b200_multi_cfg {
+    int32_t device;       /* CUDA ordinal */
+    int32_t n_streams;    /* 1..256 */
+    int32_t n_threads;    /* parser threads, 0 = one per host core (capped at n_streams) */
+    int32_t reserved[5];
+} p264b200_multi_cfg;
+
+int  p264b200_multi_open(p264b200_multi **out, const p264b200_multi_cfg *cfg);
+void p264b200_multi_close(p264b200_multi *m);
+/* whole byte stream of stream s; the buffer must stay valid and unchanged until close */
+int  p264b200_multi_set_stream(p264b200_multi *m, int s, const uint8_t *annexb, size_t bytes);
+/* Decode the next picture of every stream that still has one.  Returns the number of pictures
+ * produced (0 = every stream has ended) or a negative P264B200_E* code; produced[s] (optional,
+ * n_streams bytes) tells which streams delivered a picture in this step. */
+int  p264b200_multi_step(p264b200_multi *m, uint8_t *produced);
+/* Tight I420 picture (Y, U, V back to back, coded size) of stream s from the last step: pinned host
+ * memory owned by the decoder, valid until the next step.  NULL if the stream produced nothing. */
+const uint8_t *p264b200_multi_picture(const p264b200_multi *m, int s, int *width, int *height);
+
+/* ------------------------------------------------------------------------- *
  * Synthetic stream generator (BASELINE.json configs 3-5): emits FrameSyntax for a
  * stream of random P pictures (optionally after one intra picture).  Deterministic
  * for a given cfg.  Not part of the reference (which ships no generator or tests).

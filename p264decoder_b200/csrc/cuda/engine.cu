@@ -416,8 +416,19 @@ int p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_fr
     CK(cudaStreamWaitEvent(e->s_h2d, e->ev_recon[step], 0));
     CK(cudaMemcpyAsync(e->d_mbs + s0 * n_mb, fs[0].mbs, (size_t)n * n_mb * sizeof(p264b200_mb), cudaMemcpyHostToDevice, e->s_h2d));
     const size_t coef_span = (size_t)(n - 1) * e->coef_cap + fs[n - 1].hdr.n_coef;
-    if (coef_span)
-        CK(cudaMemcpyAsync(e->d_coefs + s0 * e->coef_cap, fs[0].coefs, coef_span * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
+    size_t coef_used = 0;
+    for (int l = 0; l < n; l++) coef_used += fs[l].hdr.n_coef;
+    if (coef_span <= 2 * coef_used + (1u << 19)) {
+        // tightly sized lanes (bench): one copy over the whole area
+        if (coef_span)
+            CK(cudaMemcpyAsync(e->d_coefs + s0 * e->coef_cap, fs[0].coefs, coef_span * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
+    } else {
+        // worst-case sized lanes (multi-stream decoder): the gaps would dominate the transfer
+        for (int l = 0; l < n; l++)
+            if (fs[l].hdr.n_coef)
+                CK(cudaMemcpyAsync(e->d_coefs + (s0 + l) * e->coef_cap, fs[l].coefs, (size_t)fs[l].hdr.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice,
+                                   e->s_h2d));
+    }
     CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
     CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
     e->h2d_busy = true;

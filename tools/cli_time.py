@@ -29,3 +29,20 @@ t_gpu, m_gpu = run(ROOT / "p264decoder_b200" / "lib" / "p264dec_b200", "/tmp/f26
 print(f"reference CLI : {t_ref:.3f} s  ({300 / t_ref:.0f} CIF frames/s)  md5 {m_ref}")
 print(f"B200 CLI      : {t_gpu:.3f} s  ({300 / t_gpu:.0f} CIF frames/s, incl. process start + CUDA context)  md5 {m_gpu}")
 print("byte-identical" if m_ref == m_gpu else "DIFFERENT")
+
+# N copies of the stream at once: the reference = N processes of its CLI on the host cores (no output file),
+# the B200 build = one p264dec_multi process, one engine lane per stream
+import os
+cores = os.cpu_count() or 1
+for n in (16, 64, 256):
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([str(REF / "p264dec_ref"), "-d", str(src)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(min(n, 64))]
+    for p in procs:
+        p.wait()
+    t_ref_n = (time.perf_counter() - t0) * (n / min(n, 64))
+    r = subprocess.run([str(ROOT / "p264decoder_b200" / "lib" / "p264dec_multi"), "-n", str(n), str(src)], capture_output=True, text=True)
+    fps = [l for l in r.stderr.splitlines() if "decoding speed" in l]
+    steady = [l for l in r.stderr.splitlines() if "after the first step" in l]
+    print(f"{n:3d} streams: reference CLI x {n} on {cores} cores {300 * n / t_ref_n:8.0f} frames/s   p264dec_multi {fps[0].split(':')[1].strip() if fps else r.stderr[-200:]}"
+          f" whole process, {steady[0].split(':')[1].strip() if steady else '?'} after CUDA context + engine creation")
+
