@@ -7,7 +7,8 @@ with
   nvdisasm --print-line-info CUBIN                        (instruction -> file:line)
 by instruction order inside the kernel's .text section.
 
-usage: ncu_lines.py REPORT.ncu-rep CUBIN KERNEL_SUBSTRING [top_n]
+usage: ncu_lines.py REPORT.ncu-rep CUBIN KERNEL_SUBSTRING [top_n] [column]
+(column: "Instructions Executed" by default; "# Samples" gives the warp-stall samples = where the time goes)
 """
 import collections
 import csv
@@ -19,6 +20,7 @@ import sys
 def main():
     rep, cubin, kname = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    col = sys.argv[5] if len(sys.argv) > 5 else "Instructions Executed"
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     counts, cur, hdr = [], None, None
@@ -30,8 +32,8 @@ def main():
         if r and r[0] == "Address":
             hdr = r
             continue
-        if cur and kname in cur and hdr and len(r) > hdr.index("Instructions Executed"):
-            counts.append((r[1].strip(), int(r[hdr.index("Instructions Executed")])))
+        if cur and kname in cur and hdr and len(r) > hdr.index(col):
+            counts.append((r[1].strip(), int(r[hdr.index(col)])))
     dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.splitlines()
     lines, in_k, loc = [], False, ("?", 0)
     for l in dis:
@@ -56,7 +58,7 @@ def main():
     for (loc, _), (_, n) in zip(lines, counts):
         per[loc] += n
         tot += n
-    print(f"total warp-instructions executed: {tot}")
+    print(f"total {col}: {tot}")
     for loc, n in per.most_common(top):
         print(f"{100 * n / tot:6.2f}%  {n:12d}  {loc[0]}:{loc[1]}")
 
