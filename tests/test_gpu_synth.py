@@ -70,6 +70,13 @@ def test_lanes_batched():
     _run_stream(9, 7, 5, lanes=5, n_refs=2, seed=11, intra_pct=8)
 
 
+@pytest.mark.parametrize("mb_w,mb_h", [(1, 1), (2, 1), (1, 3), (3, 2), (1, 9), (9, 1), (5, 17)])
+def test_tiny_and_ragged_geometries(mb_w, mb_h):
+    # pictures smaller than one recon_inter tile (8x4 MBs), narrower than the deblock ring (4 MBs), a single
+    # macroblock row / column, and 17 rows = two full deblock row groups + one row
+    _run_stream(mb_w, mb_h, 4, lanes=3, n_refs=2, seed=31 + mb_w * 7 + mb_h, intra_pct=15, sweep_offsets=1, mv_range=6)
+
+
 def test_tall_picture_many_lanes_dense_intra():
     # 19 macroblock rows = three deblock row groups (8 + 8 + 3), 9 lanes = two full stream quads + one lane,
     # 40 % intra macroblocks = long intra runs with intra neighbours above (the per-macroblock wait path)
