@@ -260,9 +260,15 @@ __device__ __forceinline__ long long dbf_now_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// (compiled in only with -DP264B200_DBF_TRACE: the four predicate tests per macroblock were 3 % of the kernel's instructions)
+#ifdef P264B200_DBF_TRACE
+constexpr bool kDbfTraceOn = true;
+#else
+constexpr bool kDbfTraceOn = false;
+#endif
 __device__ __forceinline__ void dbf_mark(bool on, int w, int s, int k)
 {
-    if (on && s < kDbfTraceSteps && (threadIdx.x & 31) == 0) g_dbf_trace[w][s][k] = clock64();
+    if (kDbfTraceOn && on && s < kDbfTraceSteps && (threadIdx.x & 31) == 0) g_dbf_trace[w][s][k] = clock64();
 }
 
 // ---- shared-memory transaction barriers (mbarrier), one arriving thread per phase -------------------
@@ -295,6 +301,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
         "r"(parity), "r"(kDbfSuspendNs)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ int lds_acquire(const int *p)
 {
     int v;
@@ -313,7 +333,6 @@ struct DbfSmem {
                                                                  // chroma: plane p rows 6,7 at 16p + 8k
     uint64_t full[kDbfRows + 1][kDbfRing];                       // ring[i][k] holds the rows of its next macroblock
     uint64_t empty[kDbfRows + 1][kDbfRing];                      // the consumer is done with ring[i][k]
-    int stored;                                                  // macroblocks of the CTA's last row that are in global memory
     int ticket;
 };
 
@@ -437,7 +456,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     const DeblockSide *side = fd.dbf_bs + (size_t)row * g.mb_w;
     uint8_t *T = sm.tile[w][sub] + (C ? 64 * pl : 0);
     // rows this thread stores itself / hands to the row below through the ring
-    const bool store_a = !(bottom_smem && 2 * j > NR - TR), store_b = !(bottom_smem && 2 * j + 1 > NR - TR);
+    const bool store_a = !(bottom_smem && 2 * j > NR - TR), store_b = !(bottom_smem && 2 * j + 1 > NR - TR);   // (a publishing row stores everything itself)
     const bool to_ring = bottom_smem && 2 * j >= NR - TR;
     const int ring_off = (C ? 16 * pl : 0) + RB * (2 * j - (NR - TR));
 
@@ -461,7 +480,8 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         vec_set(vb, prev[1]);
         if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * m) = va;
         if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * m) = vb;
-        if (bottom_smem) {
+        if (bottom_smem || publishes) {
+            // (the CTA's last row hands over to the out thread the same way, without data: ring index kDbfRows)
             mbar_wait(&sm.empty[w + 1][m & RM], ((m / kDbfRing) & 1) ^ 1);
             if (to_ring) {
                 uint8_t *slot = sm.ring[w + 1][m & RM][sub] + ring_off;
@@ -470,9 +490,6 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.full[w + 1][m & RM]);
-        } else if (publishes) {
-            __syncwarp();
-            if (lane == 0) sts_release(&sm.stored, m + 1);
         }
     };
 
@@ -482,7 +499,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
     for (int x = 0; x < g.mb_w; x++) {
         const bool last = x == g.mb_w - 1;
         dbf_mark(trace, w, x, 0);
-        if (times_on && threadIdx.x == 0 && (x == 0 || last)) g_dbf_cta_ns[tk][x == 0 ? 1 : 2] = dbf_now_ns();
+        if (kDbfTraceOn && times_on && threadIdx.x == 0 && (x == 0 || last)) g_dbf_cta_ns[tk][x == 0 ? 1 : 2] = dbf_now_ns();
         // ---- prefetch the next macroblock's rows, strengths and parameters (and, once per 128-byte line, pull
         // the next line into L2 so that those loads do not wait on HBM inside the dependent chain)
         if (act && (x & (128 / RB - 1)) == 0 && x + 128 / RB < g.mb_w) {
@@ -589,7 +606,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         }
         if (last) hand_off(x);
         dbf_mark(trace, w, x, 3);
-        if (trace) {
+        if (kDbfTraceOn && trace) {
             // diagnostics only: split the wait for the prefetched side info from the wait for the prefetched rows
             uint32_t d;
             asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(bsw_n), "r"(prm_n.x ^ prm_n.z));
@@ -652,23 +669,23 @@ __device__ __forceinline__ void deblock_in_warp(DbfSmem &sm, const FrameDesc *__
 }
 
 // The "out" thread of a CTA that has a row group below it: publishes how many macroblocks of the CTA's last row
-// are in global memory.  The last row's lanes store, __syncwarp, lane 0 releases sm.stored (cta scope); this
-// thread acquires it, fences at gpu scope and releases the progress word (cumulativity carries the stores).
+// are in global memory.  It is the consumer of that row's (data-less) hand-off ring: the row's lanes store,
+// __syncwarp, lane 0 arrives (release.cta); this thread's wait acquires, and its release.gpu store of the progress
+// word is cumulative over those stores.  Whatever has arrived meanwhile is published in one go.
 __device__ __forceinline__ void deblock_out_thread(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int quad, int grp, bool chroma)
 {
+    constexpr int RM = kDbfRing - 1;
     const int row_last = grp * kDbfRows + kDbfRows - 1;
     if (row_last + 1 >= g.mb_h) return;
     int *prog = descs[kDbfQuad * quad].row_progress + (chroma ? 2 : 1) * g.mb_h + row_last;
-    int published = 0, spins = 0;
-    while (published < g.mb_w) {
-        const int c = lds_acquire(&sm.stored);
-        if (c > published) {
-            st_release(prog, c);   // release.gpu is cumulative over what the acquire above made visible
-            published = c;
-            spins = 0;
-            __nanosleep(1000);   // the next macroblock is ~2 us away
-        } else
-            __nanosleep(++spins < 8 ? 200 : 400);
+    int m = 0;
+    while (m < g.mb_w) {
+        mbar_wait(&sm.full[kDbfRows][m & RM], (m / kDbfRing) & 1);
+        int hi = m + 1;
+        while (hi < g.mb_w && hi < m + kDbfRing && mbar_test(&sm.full[kDbfRows][hi & RM], (hi / kDbfRing) & 1)) hi++;
+        for (int k = m; k < hi; k++) mbar_arrive(&sm.empty[kDbfRows][k & RM]);
+        st_release(prog, hi);   // release.gpu is cumulative over what the waits above made visible
+        m = hi;
     }
 }
 
@@ -693,7 +710,6 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
             u = atomicAdd(sync + 1 + role, 1);
         }
         sm.ticket = 2 * u + role;
-        sm.stored = 0;
         for (int i = 0; i < (kDbfRows + 1) * kDbfRing; i++) {
             mbar_init(&sm.full[0][0] + i, 1);
             mbar_init(&sm.empty[0][0] + i, 1);
@@ -709,7 +725,7 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
     const int grp = u / quads, quad = u - grp * quads;
     const bool trace = tk == trace_ticket;
     const bool times = trace_ticket >= 0 && tk < 2048 && threadIdx.x == 0;
-    if (times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
+    if (kDbfTraceOn && times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
     const int w = threadIdx.x >> 5;
     if (w == kDbfRows) {
         if (grp > 0) {
@@ -728,7 +744,7 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
         deblock_rows<false>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
     else
         deblock_rows<true>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
-    if (times) g_dbf_cta_ns[tk][3] = dbf_now_ns();
+    if (kDbfTraceOn && times) g_dbf_cta_ns[tk][3] = dbf_now_ns();
 }
 #endif  // P264B200_DEFINE_KERNELS
 

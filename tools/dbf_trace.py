@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-step cycle trace of one deblock CTA (needs a GPU).
+"""Per-step cycle trace of one deblock CTA (needs a GPU and a library built with `make -C p264decoder_b200/csrc TRACE=1`).
 
 usage: P264B200_TRACE=<ticket> python tools/dbf_trace.py [lanes]
 Runs a few 1080p steps, then prints for every warp of the traced CTA the mean cycles per lockstep step spent
