@@ -87,13 +87,24 @@ __device__ __forceinline__ void unscan_dequant(const int16_t *__restrict__ lvl, 
     const int s0 = 16 * c_dq_scale[rem][0], s1 = 16 * c_dq_scale[rem][1], s2 = 16 * c_dq_scale[rem][2];
     // raster positions in zig-zag order: {0,1,4,8,5,2,3,6,9,12,13,10,7,11,14,15}
     const int zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    if (qbits >= 0) {
+        // qp >= 24 (uniform over a picture in practice): the left shift folds into the multiplier, the int16
+        // truncation sees the same low 16 bits
+        const int m0 = (int)((unsigned)s0 << qbits), m1 = (int)((unsigned)s1 << qbits), m2 = (int)((unsigned)s2 << qbits);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int r = zz[i], x = r & 3, y = r >> 2;
-        const int mf = ((x & 1) + (y & 1)) == 0 ? s0 : (((x & 1) + (y & 1)) == 1 ? s1 : s2);
-        int t = v[i] * mf;
-        t = qbits >= 0 ? (int)((unsigned)t << qbits) : ((t + (1 << (-qbits - 1))) >> (-qbits));
-        d[r] = (short)t;
+        for (int i = 0; i < 16; i++) {
+            const int r = zz[i], x = r & 3, y = r >> 2;
+            const int mf = ((x & 1) + (y & 1)) == 0 ? m0 : (((x & 1) + (y & 1)) == 1 ? m1 : m2);
+            d[r] = (short)(v[i] * mf);
+        }
+    } else {
+        const int sh = -qbits, rnd = 1 << (sh - 1);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int r = zz[i], x = r & 3, y = r >> 2;
+            const int mf = ((x & 1) + (y & 1)) == 0 ? s0 : (((x & 1) + (y & 1)) == 1 ? s1 : s2);
+            d[r] = (short)((v[i] * mf + rnd) >> sh);
+        }
     }
 }
 
