@@ -321,7 +321,7 @@ struct InterSmem {
     int nres[2];                                    // full / DC-only residual blocks
 };
 
-__global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x)
+__global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x)
 {
     __shared__ __align__(16) InterSmem sm;
     const FrameDesc &fd = descs[blockIdx.y];
