@@ -93,7 +93,8 @@ typedef struct p264b200_synth_cfg {
     int32_t  chroma_qp_index_offset;
     int32_t  confine_mv;        /* keep referenced samples inside the reference's 32-sample border      */
     int32_t  first_intra;       /* picture 0 is an all-intra picture                                    */
-    int32_t  reserved[4];
+    int32_t  intra_period;      /* > 0 (with first_intra): every intra_period-th picture is all-intra   */
+    int32_t  reserved[3];
 } p264b200_synth_cfg;
 
 void p264b200_synth_default(p264b200_synth_cfg *cfg, int mb_w, int mb_h);
@@ -101,6 +102,20 @@ p264b200_synth *p264b200_synth_open(const p264b200_synth_cfg *cfg);
 void p264b200_synth_close(p264b200_synth *s);
 /* next picture; *out points at generator-owned buffers valid until the next call */
 int  p264b200_synth_next(p264b200_synth *s, p264b200_frame_syntax *out);
+
+/* ------------------------------------------------------------------------- *
+ * Bitstream writer (test / benchmark infrastructure): turns FrameSyntax
+ * pictures into a real Baseline / CAVLC Annex-B stream that the UNMODIFIED reference decoder can
+ * decode -- the inverse of the parser.  Restricted to what the stock decoder handles: the first
+ * picture intra, one reference frame, partitions >= 8x8, one QP per picture.  P_SKIP records are
+ * written as P_L0 16x16 without residual (same reconstruction).  No GPU needed.
+ * ------------------------------------------------------------------------- */
+typedef struct p264b200_writer p264b200_writer;
+p264b200_writer *p264b200_writer_open(int mb_w, int mb_h, int chroma_qp_index_offset);
+void p264b200_writer_close(p264b200_writer *w);
+/* appends one picture (SPS + PPS first when it is an intra picture); returns the bytes appended or < 0 */
+int  p264b200_writer_put(p264b200_writer *w, const p264b200_frame_syntax *fs);
+const uint8_t *p264b200_writer_data(const p264b200_writer *w, size_t *bytes);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -102,7 +102,8 @@ class SynthCfg(C.Structure):
         ("chroma_qp_index_offset", C.c_int32),
         ("confine_mv", C.c_int32),
         ("first_intra", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("intra_period", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -283,6 +284,41 @@ class Synth:
 
     def next(self) -> Frame:
         return Frame.from_syntax(self.next_syntax())
+
+
+class Writer:
+    """Annex-B bitstream writer (csrc/host/writer.cc): FrameSyntax pictures -> a stream the unmodified
+    reference decoder can decode.  Test / benchmark infrastructure."""
+
+    def __init__(self, mb_w, mb_h, chroma_qp_index_offset=0):
+        lib = self._lib = load_library()
+        lib.p264b200_writer_open.restype = C.c_void_p
+        lib.p264b200_writer_open.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.p264b200_writer_close.argtypes = [C.c_void_p]
+        lib.p264b200_writer_put.argtypes = [C.c_void_p, C.POINTER(FrameSyntax)]
+        lib.p264b200_writer_data.restype = C.c_void_p
+        lib.p264b200_writer_data.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        self._w = lib.p264b200_writer_open(mb_w, mb_h, chroma_qp_index_offset)
+        if not self._w:
+            raise P264Error("p264b200_writer_open failed")
+
+    def put(self, fs: "FrameSyntax") -> int:
+        n = self._lib.p264b200_writer_put(self._w, C.byref(fs))
+        if n < 0:
+            raise P264Error(f"p264b200_writer_put failed ({n}): the picture is outside what the stock decoder can decode")
+        return n
+
+    def data(self) -> bytes:
+        n = C.c_size_t()
+        p = self._lib.p264b200_writer_data(self._w, C.byref(n))
+        return C.string_at(p, n.value)
+
+    def close(self):
+        if getattr(self, "_w", None):
+            self._lib.p264b200_writer_close(self._w)
+            self._w = None
+
+    __del__ = close
 
 
 def smooth_picture(width, height, seed=0):

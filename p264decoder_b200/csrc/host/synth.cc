@@ -121,11 +121,13 @@ int p264b200_synth_next(p264b200_synth *s, p264b200_frame_syntax *out)
     const p264b200_synth_cfg &c = s->cfg;
     Rng &r = s->rng;
     const int n_slots = c.n_refs + 1;
-    const bool iframe = s->frame == 0 && c.first_intra;
+    const bool iframe = c.first_intra && (s->frame == 0 || (c.intra_period > 0 && s->frame % c.intra_period == 0));
     const int steps = c.qp_step > 0 ? (c.qp_max - c.qp_min) / c.qp_step + 1 : 1;
     const int qp = c.qp_min + (c.qp_step > 0 ? (s->frame % steps) * c.qp_step : 0);
     const int W = 16 * c.mb_w, H = 16 * c.mb_h;
-    const int num_ref = iframe ? 0 : (s->frame < c.n_refs ? (s->frame > 0 ? s->frame : 1) : c.n_refs);
+    // pictures since the last intra picture bound the list (an IDR empties the DPB)
+    const int since = c.first_intra && c.intra_period > 0 ? s->frame % c.intra_period : s->frame;
+    const int num_ref = iframe ? 0 : (since < c.n_refs ? (since > 0 ? since : 1) : c.n_refs);
     s->coefs.clear();
     int n_intra = 0;
 

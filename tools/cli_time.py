@@ -16,7 +16,7 @@ def run(exe, out, n=3):
     best = None
     for _ in range(n):
         t0 = time.perf_counter()
-        r = subprocess.run([str(exe), "-d", str(src), out], capture_output=True, text=True)
+        r = subprocess.run([str(exe), "-d", str(globals()["src"]), out], capture_output=True, text=True)
         dt = time.perf_counter() - t0
         if r.returncode:
             sys.exit(f"{exe} failed: {r.stderr[-400:]}")
@@ -46,3 +46,25 @@ for n in (16, 64, 256):
     print(f"{n:3d} streams: reference CLI x {n} on {cores} cores {300 * n / t_ref_n:8.0f} frames/s   p264dec_multi {fps[0].split(':')[1].strip() if fps else r.stderr[-200:]}"
           f" whole process, {steady[0].split(':')[1].strip() if steady else '?'} after CUDA context + engine creation")
 
+
+# the same on a synthetic 1080p stream (BASELINE.json configs[2] as a real bitstream, tools/make_stream.py)
+sys.path.insert(0, str(ROOT / "tools"))
+import make_stream  # noqa: E402
+
+src = Path("/tmp/synth1080.264")
+n_pic = 48
+make_stream.make(src, "1080p", n_pic)
+t_ref, m_ref = run(REF / "p264dec_ref", "/tmp/s1080_ref.yuv", n=2)
+t_gpu, m_gpu = run(ROOT / "p264decoder_b200" / "lib" / "p264dec_b200", "/tmp/s1080_b200.yuv", n=2)
+print(f"1080p synthetic stream, {n_pic} pictures: reference CLI {n_pic / t_ref:.1f} pictures/s, B200 CLI {n_pic / t_gpu:.1f} pictures/s whole process; "
+      + ("byte-identical" if m_ref == m_gpu else "DIFFERENT"))
+for n in (16, 64):
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([str(REF / "p264dec_ref"), "-d", str(src)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(min(n, cores))]
+    for p in procs:
+        p.wait()
+    t_ref_n = (time.perf_counter() - t0) * (n / min(n, cores))
+    r = subprocess.run([str(ROOT / "p264decoder_b200" / "lib" / "p264dec_multi"), "-n", str(n), str(src)], capture_output=True, text=True)
+    steady = [l for l in r.stderr.splitlines() if "after the first step" in l]
+    print(f"{n:3d} x 1080p streams: reference CLI on {cores} cores {n_pic * n / t_ref_n:7.1f} pictures/s   p264dec_multi "
+          f"{steady[0].split(':')[1].strip() if steady else r.stderr[-200:]} after CUDA context + engine creation")
