@@ -20,8 +20,15 @@ public:
         if (n <= 0) return 0;
         size_t byte = pos_ >> 3;
         int sh = pos_ & 7;
-        uint64_t w = 0;
         size_t nbytes = size_bits_ >> 3;
+        if (byte + 8 <= nbytes) {
+            // fast path: one unaligned big-endian 64-bit load (the host parser is the bottleneck of real-bitstream decode)
+            uint64_t w;
+            __builtin_memcpy(&w, p_ + byte, 8);
+            w = __builtin_bswap64(w);
+            return (uint32_t)((w << sh) >> (64 - n));
+        }
+        uint64_t w = 0;
         for (int i = 0; i < 5; i++) w = (w << 8) | (byte + i < nbytes ? p_[byte + i] : 0);
         return (uint32_t)((w >> (40 - sh - n)) & ((1ull << n) - 1));
     }
@@ -43,6 +50,13 @@ public:
 
     // Exp-Golomb ue(v); the leading-zero scan is capped at 32 like core/bs.h:143-152
     int ue() {
+        // codes of up to 25 bits (<= 12 leading zeros) straight from one window; longer / truncated ones bit by bit
+        const uint32_t w = show(25);
+        if (w >> 12) {
+            const int zeros = __builtin_clz(w) - 7, len = 2 * zeros + 1;
+            skip(len);
+            return (int)((w >> (25 - len)) - 1);
+        }
         int zeros = 0;
         while (!eof() && read1() == 0 && zeros < 32) zeros++;
         if (zeros == 0) return 0;

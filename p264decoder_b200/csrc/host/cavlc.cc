@@ -100,6 +100,7 @@ struct Lut {
     uint16_t *tab;
 };
 uint16_t g_tok[4][1 << 16];
+uint16_t g_tok8[4][1 << 8];   // codes of length <= 8 only
 uint16_t g_tok_dc[1 << 8];
 uint16_t g_tz[15][1 << 9];
 uint16_t g_tz_dc[3][1 << 3];
@@ -117,7 +118,10 @@ void build()
 {
     for (int t = 0; t < 4; t++)
         for (int s = 0; s < 68; s++)
-            if ((s & 3) <= (s >> 2)) fill(g_tok[t], 16, s, kTokLen[t][s], kTokBits[t][s]);
+            if ((s & 3) <= (s >> 2)) {
+                fill(g_tok[t], 16, s, kTokLen[t][s], kTokBits[t][s]);
+                if (kTokLen[t][s] <= 8) fill(g_tok8[t], 8, s, kTokLen[t][s], kTokBits[t][s]);
+            }
     for (int s = 0; s < 20; s++)
         if ((s & 3) <= (s >> 2)) fill(g_tok_dc, 8, s, kTokDcLen[s], kTokDcBits[s]);
     for (int t = 0; t < 15; t++)
@@ -179,7 +183,13 @@ int cavlc_read_block(BitReader &br, int nC, int max_coeff, int16_t *levels)
     else {
         // nC class boundaries of Table 9-5 (decoder/dec_cavlc.c:1389-1400 uses the same split)
         const int cls = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3;
-        tok = lookup(br, g_tok[cls], 16);
+        // codes of up to 8 bits (the common ones) from a 512-byte table that stays in L1; the 128 KB flat table only for the rest
+        const uint16_t e = g_tok8[cls][br.show(8)];
+        if (e) {
+            br.skip(e & 0xff);
+            tok = e >> 8;
+        } else
+            tok = lookup(br, g_tok[cls], 16);
     }
     if (tok < 0) return -1;
     const int total = tok >> 2, t1s = tok & 3;
@@ -192,9 +202,14 @@ int cavlc_read_block(BitReader &br, int nC, int max_coeff, int16_t *levels)
     for (; i < t1s; i++) lev[i] = 1 - 2 * (int)br.read1();
     for (; i < total; i++) {
         int prefix = 0;
-        while (br.read1() == 0) {
-            if (++prefix > 32 || br.eof()) return -1;
-        }
+        const uint32_t w = br.show(25);
+        if (w >> 9) {  // at most 15 zeros before the 1: the whole prefix sits in the window
+            prefix = __builtin_clz(w) - 7;
+            br.skip(prefix + 1);
+        } else
+            while (br.read1() == 0) {
+                if (++prefix > 32 || br.eof()) return -1;
+            }
         int suffix_size = suffix_len;
         if (prefix == 14 && suffix_len == 0) suffix_size = 4;
         if (prefix >= 15) suffix_size = prefix - 3;

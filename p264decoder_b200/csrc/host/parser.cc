@@ -593,13 +593,11 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
     int16_t luma[16][16];  // raster block index
     int16_t dc[16], cdc[2][4], cac[8][16];
     int tot_luma[16];
-    memset(luma, 0, sizeof(luma));
-    memset(dc, 0, sizeof(dc));
-    memset(cdc, 0, sizeof(cdc));
-    memset(cac, 0, sizeof(cac));
+    // (blocks are cleared only when they are about to be read: three quarters of the 8x8s carry nothing)
     const bool i16 = m.mb_type == P264B200_MB_I16x16;
 
     if (i16) {
+        memset(dc, 0, sizeof(dc));
         const int nC = predict_nnz(nnz_y_.data(), s4, 4 * mbx, 4 * mby);
         if (cavlc_read_block(br, nC, 16, dc) < 0) return P264B200_EBITSTREAM;
     }
@@ -608,6 +606,7 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
         const int gx = 4 * mbx + bx, gy = 4 * mby + by;
         int tot = 0;
         if (cbp_luma & (1 << (i / 4))) {
+            memset(luma[b], 0, sizeof(luma[b]));
             const int nC = predict_nnz(nnz_y_.data(), s4, gx, gy);
             tot = i16 ? cavlc_read_block(br, nC, 15, luma[b] + 1) : cavlc_read_block(br, nC, 16, luma[b]);
             if (tot < 0) return P264B200_EBITSTREAM;
@@ -617,6 +616,7 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
     }
     int tot_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (m.cbp_chroma & 3) {
+        memset(cdc, 0, sizeof(cdc));
         if (cavlc_read_block(br, -1, 4, cdc[0]) < 0 || cavlc_read_block(br, -1, 4, cdc[1]) < 0)
             return P264B200_EBITSTREAM;
     }
@@ -625,6 +625,7 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
             const int gx = 2 * mbx + (i & 1), gy = 2 * mby + (i >> 1);
             int tot = 0;
             if (m.cbp_chroma & 2) {
+                memset(cac[c * 4 + i], 0, sizeof(cac[0]));
                 const int nC = predict_nnz(nnz_c_[c].data(), s2, gx, gy);
                 tot = cavlc_read_block(br, nC, 15, cac[c * 4 + i] + 1);
                 if (tot < 0) return P264B200_EBITSTREAM;
