@@ -142,7 +142,16 @@ inline int lookup(BitReader &br, const uint16_t *tab, int bits)
 
 }  // namespace
 
-void cavlc_init() { std::call_once(g_once, build); }
+EmptyToken g_empty_token[5];
+
+void cavlc_init()
+{
+    std::call_once(g_once, [] {
+        build();
+        for (int t = 0; t < 4; t++) g_empty_token[t] = EmptyToken{(uint8_t)kTokLen[t][0], (uint8_t)kTokBits[t][0]};
+        g_empty_token[4] = EmptyToken{(uint8_t)kTokDcLen[0], (uint8_t)kTokDcBits[0]};
+    });
+}
 
 // raw table access for the table self-check (tests compare these with the standard's code words)
 int cavlc_table_entry(int kind, int table, int sym, int *len, int *bits)

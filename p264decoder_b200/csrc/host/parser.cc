@@ -606,10 +606,12 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
         const int gx = 4 * mbx + bx, gy = 4 * mby + by;
         int tot = 0;
         if (cbp_luma & (1 << (i / 4))) {
-            memset(luma[b], 0, sizeof(luma[b]));
             const int nC = predict_nnz(nnz_y_.data(), s4, gx, gy);
-            tot = i16 ? cavlc_read_block(br, nC, 15, luma[b] + 1) : cavlc_read_block(br, nC, 16, luma[b]);
-            if (tot < 0) return P264B200_EBITSTREAM;
+            if (!cavlc_skip_empty(br, nC)) {
+                memset(luma[b], 0, sizeof(luma[b]));
+                tot = i16 ? cavlc_read_block(br, nC, 15, luma[b] + 1) : cavlc_read_block(br, nC, 16, luma[b]);
+                if (tot < 0) return P264B200_EBITSTREAM;
+            }
         }
         nnz_y_[gy * s4 + gx] = (uint8_t)tot;
         tot_luma[b] = tot;
@@ -625,10 +627,12 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
             const int gx = 2 * mbx + (i & 1), gy = 2 * mby + (i >> 1);
             int tot = 0;
             if (m.cbp_chroma & 2) {
-                memset(cac[c * 4 + i], 0, sizeof(cac[0]));
                 const int nC = predict_nnz(nnz_c_[c].data(), s2, gx, gy);
-                tot = cavlc_read_block(br, nC, 15, cac[c * 4 + i] + 1);
-                if (tot < 0) return P264B200_EBITSTREAM;
+                if (!cavlc_skip_empty(br, nC)) {
+                    memset(cac[c * 4 + i], 0, sizeof(cac[0]));
+                    tot = cavlc_read_block(br, nC, 15, cac[c * 4 + i] + 1);
+                    if (tot < 0) return P264B200_EBITSTREAM;
+                }
             }
             nnz_c_[c][gy * s2 + gx] = (uint8_t)tot;
             tot_c[c * 4 + i] = tot;
