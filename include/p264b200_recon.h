@@ -185,10 +185,11 @@ int  p264b200_profile_read(p264b200_engine *e, float ms_out[8], uint64_t launche
 /* number of kernel launches issued by the engine since creation */
 uint64_t p264b200_engine_launches(const p264b200_engine *e);
 
-/* Diagnostics: with P264B200_TRACE=<ticket> in the environment the deblock CTA that drew that ticket records
- * clock64() marks per warp and step ([9 warps][320 steps][4 marks] int64); this copies them out. */
+/* Diagnostics (library built with `make TRACE=1` only; otherwise the buffers stay zero): with P264B200_TRACE=<ticket> in
+ * the environment the deblock CTA that drew that ticket records clock64() marks per row warp and macroblock
+ * ([9][320 macroblocks][6 marks] int64); this copies them out (tools/dbf_trace.py). */
 int  p264b200_debug_trace(void *dst, size_t bytes);
-/* ... and every deblock CTA records %globaltimer (ns) at entry / first step / last step / exit: [2048 tickets][4] int64 */
+/* ... and every deblock CTA records %globaltimer (ns) at entry / first macroblock / last macroblock / exit: [2048 tickets][4] int64 */
 int  p264b200_debug_cta_times(void *dst, size_t bytes);
 
 /* pinned host memory helpers for the callers that pack FrameSyntax */
