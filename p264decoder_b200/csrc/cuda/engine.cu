@@ -478,7 +478,7 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         if (pslice) {
             ProfScope p(e, K_INTER, st);
             const int tiles_x = (g.mb_w + kTileW - 1) / kTileW, tiles_y = (g.mb_h + kTileH - 1) / kTileH;
-            recon_inter_kernel<<<dim3(tiles_x * tiles_y, nl), kInterThreads, 0, st>>>(descs, g, tiles_x);
+            recon_inter_kernel<<<dim3(tiles_x * tiles_y, nl), kInterThreads, 0, st>>>(descs, g, tiles_x, e->dbg);
         }
         if (G > 1) CK(cudaEventRecord(e->ev_mc[gi], st));
         if (dbf) {
