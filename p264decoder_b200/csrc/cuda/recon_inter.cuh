@@ -324,7 +324,7 @@ struct InterSmem {
 __global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x, int dbg)
 {
     // dbg (engine knob P264B200_DBG, timing experiments only -- the pictures are wrong when set): bit 0 no luma prediction,
-    // bit 1 no chroma prediction, bit 2 no residual.  Round 1 at 256 lanes: all 1.72 ms, no luma 0.86, no chroma 1.38, no
+    // bit 1 no chroma prediction (bit 3 / 4: only without the per-cell / one-MV chroma blocks: 0.15 / 0.16 ms), bit 2 no residual.  Round 1 at 256 lanes: all 1.72 ms, no luma 0.86, no chroma 1.38, no
     // residual 1.43, none of the three (staging + bucketing + barriers + copy-out) 0.43 ms
     __shared__ __align__(16) InterSmem sm;
     const FrameDesc &fd = descs[blockIdx.y];
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const Fra
         const int n_one = sm.cnt[6], n_cell = sm.cnt[7];
         const bool one = tid < n_one;
         // one-MV quadrants fill the list (= the warps) from the front, per-cell quadrants from the back
-        if ((one || tid >= 8 * kTileMbs - n_cell) && !(dbg & 2)) {
+        if ((one || tid >= 8 * kTileMbs - n_cell) && !(dbg & 2) && !((dbg & 8) && !one) && !((dbg & 16) && one)) {
             const int q = sm.cperm[tid];
             const int mb = q >> 3, cb = q & 7, plane = cb >> 2, i = cb & 3;
             const p264b200_mb &m = sm.mb[mb];
