@@ -84,8 +84,10 @@ struct p264b200_engine {
     static constexpr int kMaxGroups = 8;
     static constexpr int kSyncHdr = 4 + kDbfSmSlots;  // per lane group: intra ticket, luma / chroma deblock tickets, pad, per-SM arrival counters
     int n_groups = 1;
-    cudaStream_t gstream[kMaxGroups] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {};
+    cudaStream_t gstream[kMaxGroups] = {};   // low priority: recon_inter of the group
+    cudaStream_t hstream[kMaxGroups] = {};   // high priority: bS pre-pass, intra, deblock, border of the group
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {}, ev_hi_done[kMaxGroups] = {};
+    int dbf_pad_bytes = 0;   // P264B200_DBF_PAD (KB): dynamic shared memory added to deblock CTAs = fewer of them per SM, room for recon_inter CTAs
     bool groups_dirty = false;  // group streams hold work the main stream has not joined yet
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
     int trace_ticket = -1;  // P264B200_TRACE: deblock CTA (by ticket) whose per-step cycle marks are recorded
@@ -134,7 +136,7 @@ cudaError_t join_groups(p264b200_engine *e)
 {
     if (!e->groups_dirty) return cudaSuccess;
     for (int gi = 0; gi < e->n_groups; gi++) {
-        cudaError_t err = cudaEventRecord(e->ev_join[gi], e->gstream[gi]);
+        cudaError_t err = cudaEventRecord(e->ev_join[gi], e->hstream[gi]);
         if (err == cudaSuccess) err = cudaStreamWaitEvent(e->stream, e->ev_join[gi], 0);
         if (err != cudaSuccess) return err;
     }
@@ -216,7 +218,9 @@ void p264b200_engine_destroy(p264b200_engine *e)
     for (int gi = 0; gi < p264b200_engine::kMaxGroups; gi++) {
         if (e->ev_join[gi]) cudaEventDestroy(e->ev_join[gi]);
         if (e->ev_mc[gi]) cudaEventDestroy(e->ev_mc[gi]);
+        if (e->ev_hi_done[gi]) cudaEventDestroy(e->ev_hi_done[gi]);
         if (e->gstream[gi]) cudaStreamDestroy(e->gstream[gi]);
+        if (e->hstream[gi]) cudaStreamDestroy(e->hstream[gi]);
     }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -239,7 +243,10 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     e->cfg = *cfg;
     if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
     if (const char *d = getenv("P264B200_TRACE")) e->trace_ticket = atoi(d);
-    e->n_groups = 1;  // measured: overlapping groups does not pay while both kernels are ALU-issue bound
+    // measured (256 lanes x 1080p): 1 group 3.05 ms per step; 2 groups pipelined across steps (one group's deblock beside the
+    // other's recon_inter, priority streams) 3.15 ms; with deblock held to one CTA per SM (P264B200_DBF_PAD=100) 3.46 ms; 4 groups
+    // 3.63 ms -- both kernels lean on the same L1 / shared-memory data pipe (82 % and 67 % alone), so sharing the SMs buys nothing
+    e->n_groups = 1;
     if (const char *gq = getenv("P264B200_GROUPS")) e->n_groups = atoi(gq);
     if (e->n_groups < 1) e->n_groups = 1;
     if (e->n_groups > p264b200_engine::kMaxGroups) e->n_groups = p264b200_engine::kMaxGroups;
@@ -294,8 +301,16 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char *pad = getenv("P264B200_DBF_PAD")) e->dbf_pad_bytes = atoi(pad) * 1024;
+    if (!rc && e->dbf_pad_bytes > 0 &&
+        (err = cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->dbf_pad_bytes)) != cudaSuccess)
+        fail("cudaFuncSetAttribute", err);
     for (int gi = 0; gi < e->n_groups && !rc && e->n_groups > 1; gi++) {
-        if ((err = cudaStreamCreateWithFlags(&e->gstream[gi], cudaStreamNonBlocking)) != cudaSuccess) fail("group stream", err);
+        if ((err = cudaStreamCreateWithPriority(&e->gstream[gi], cudaStreamNonBlocking, prio_lo)) != cudaSuccess) fail("group stream", err);
+        if (!rc && (err = cudaStreamCreateWithPriority(&e->hstream[gi], cudaStreamNonBlocking, prio_hi)) != cudaSuccess) fail("group stream", err);
+        if (!rc && (err = cudaEventCreateWithFlags(&e->ev_hi_done[gi], cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
         if (!rc && (err = cudaEventCreateWithFlags(&e->ev_join[gi], cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
         if (!rc && (err = cudaEventCreateWithFlags(&e->ev_mc[gi], cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
     }
@@ -441,15 +456,19 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
     CK(cudaSetDevice(e->cfg.device));
     const Geometry &g = e->g;
     const int n_mb = g.mb_w * g.mb_h;
-    CK(cudaStreamWaitEvent(e->stream, e->ev_staged[step], 0));
-    for (int sl = 0; sl < e->cfg.n_slots; sl++)
-        if (e->step_dst_mask[step] >> sl & 1) CK(cudaStreamWaitEvent(e->stream, e->ev_d2h_slot[sl], 0));
     const FrameDesc *descs0 = e->d_descs + (size_t)step * e->cfg.lanes;
     const int G = n_lanes >= 2 * e->n_groups ? e->n_groups : 1;
-    // the group streams run ahead of each other across steps (no per-step barrier): a group only
-    // waits for the staging copies issued on the main stream so far and for its own previous work
-    if (G > 1) CK(cudaEventRecord(e->ev_fork, e->stream));
-    else {
+    // G > 1: the group streams run ahead of each other ACROSS steps (no per-step barrier): a group waits for the staging
+    // copy of this step, for the downloads of the slots it overwrites and for its own previous picture, nothing else --
+    // so one group's deblock wavefront (ALU / latency bound) shares the SMs with the other group's recon_inter (L1 bound)
+    auto wait_inputs = [&](cudaStream_t st) -> cudaError_t {
+        cudaError_t err = cudaStreamWaitEvent(st, e->ev_staged[step], 0);
+        for (int sl = 0; sl < e->cfg.n_slots && err == cudaSuccess; sl++)
+            if (e->step_dst_mask[step] >> sl & 1) err = cudaStreamWaitEvent(st, e->ev_d2h_slot[sl], 0);
+        return err;
+    };
+    if (G == 1) {
+        CK(wait_inputs(e->stream));
         CK(join_groups(e));
         CK(cudaMemsetAsync(e->d_sync, 0, e->sync_bytes, e->stream));
     }
@@ -460,14 +479,12 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         const int l0 = gi * per, l1 = l0 + per < n_lanes ? l0 + per : n_lanes;
         if (l0 >= l1) break;
         const int nl = l1 - l0;
-        cudaStream_t st = G > 1 ? e->gstream[gi] : e->stream;
+        cudaStream_t st = G > 1 ? e->gstream[gi] : e->stream;   // recon_inter
+        cudaStream_t sh = G > 1 ? e->hstream[gi] : e->stream;   // everything after it
         if (G > 1) {
-            CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-            // wavefront state of this group's lanes + its tickets
-            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * gi, 0, p264b200_engine::kSyncHdr * sizeof(int), st));
-            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), st));
-            // stagger: this group's MC starts when the previous group's MC is done, so that MC (issue-bound)
-            // of one group overlaps the latency-bound wavefronts of the others instead of all groups moving in phase
+            CK(wait_inputs(st));
+            CK(cudaStreamWaitEvent(st, e->ev_hi_done[gi], 0));   // the group's previous picture (its reference) is finished
+            // stagger: this group's MC starts when the previous group's MC is done, so that the groups do not move in phase
             if (gi > 0) CK(cudaStreamWaitEvent(st, e->ev_mc[gi - 1], 0));
         }
         unsigned flags = 0;
@@ -480,7 +497,14 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
             const int tiles_x = (g.mb_w + kTileW - 1) / kTileW, tiles_y = (g.mb_h + kTileH - 1) / kTileH;
             recon_inter_kernel<<<dim3(tiles_x * tiles_y, nl), kInterThreads, 0, st>>>(descs, g, tiles_x, e->dbg);
         }
-        if (G > 1) CK(cudaEventRecord(e->ev_mc[gi], st));
+        if (G > 1) {
+            CK(cudaEventRecord(e->ev_mc[gi], st));
+            CK(cudaStreamWaitEvent(sh, e->ev_mc[gi], 0));
+            // wavefront state of this group's lanes + its tickets
+            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * gi, 0, p264b200_engine::kSyncHdr * sizeof(int), sh));
+            CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), sh));
+        }
+        st = sh;
         if (dbf) {
             ProfScope p(e, K_DEBLOCK_BS, st);
             deblock_bs_kernel<<<dim3((n_mb + 127) / 128, nl), 128, 0, st>>>(descs, g);
@@ -494,14 +518,17 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, 0, st>>>(descs, g, nl, tickets, e->trace_ticket);
+            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, G > 1 ? e->dbf_pad_bytes : 0, st>>>(descs, g, nl, tickets, e->trace_ticket);
         }
         {
             ProfScope p(e, K_BORDER, st);
             dim3 grid((words + 255) / 256, nl);
             border_kernel<<<grid, 256, 0, st>>>(descs, g, nullptr, nullptr, nullptr);
         }
-        if (G > 1) e->groups_dirty = true;
+        if (G > 1) {
+            CK(cudaEventRecord(e->ev_hi_done[gi], sh));
+            e->groups_dirty = true;
+        }
     }
     if (G > 1) CK(join_groups(e));
     CK(cudaEventRecord(e->ev_recon[step], e->stream));
