@@ -87,6 +87,36 @@ def test_1080p_stream():
     _run_stream(120, 68, 3, n_refs=1, seed=264, intra_pct=2)
 
 
+def test_1080p_bench_shaped_many_lanes_cycled_staging():
+    """The shape bench.py times: many 1080p lanes (more deblock CTAs than fit on the machine at once), syntax pre-staged in
+    HBM, two staged pictures per lane cycled over several steps without intermediate syncs; every lane's final reference
+    ring must equal the oracle's."""
+    mb_w, mb_h, lanes, T, steps = 120, 68, 72, 2, 5
+    eng = P.Engine(mb_w, mb_h, n_slots=2, lanes=lanes, stage_steps=T)
+    rings = [O.OracleFrames(mb_w, mb_h, 2) for _ in range(lanes)]
+    staged = [[None] * lanes for _ in range(T)]
+    for l in range(lanes):
+        syn = P.Synth(mb_w, mb_h, n_refs=1, seed=900 + l, first_intra=0, confine_mv=1, intra_pct=0, coded_pct=25, max_level=8, mv_range=16,
+                      sub8x8=1, skip_pct=5, qp_min=20, qp_max=40, qp_step=2)
+        for s in range(2):
+            pic = P.smooth_picture(16 * mb_w, 16 * mb_h, seed=(l * 2 + s) % 4)
+            eng.upload(l, s, *pic)
+            rings[l].set(s, *pic)
+        for t in range(T):
+            staged[t][l] = syn.next()
+            eng.stage(t, l, staged[t][l].syntax())
+    for i in range(steps):
+        eng.recon_step(i % T, lanes)
+    eng.sync()
+    check = sorted(set([0, 1, 5, 35, 36, lanes - 5, lanes - 1]))   # the oracle needs ~30 ms per 1080p picture
+    for l in check:
+        for i in range(steps):
+            rings[l].recon(staged[i % T][l])
+        for slot in range(2):
+            _compare(eng.download(l, slot), rings[l].frames[slot], staged[0][l], f"lane {l} slot {slot} after {steps} steps")
+    eng.close()
+
+
 def test_4k_multiref_two_pictures():
     _run_stream(240, 135, 2, n_refs=4, seed=2160, sweep_offsets=1, first_intra=0)
 
