@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="1080p", choices=list(SIZES))
-    ap.add_argument("--lanes", type=int, default=256, help="independent streams per GPU per launch (the deblock wavefront ramp amortises with lanes: 64 -> 68 k, 256 -> 85 k pictures/s)")
+    ap.add_argument("--lanes", type=int, default=256, help="independent streams per GPU per launch (the deblock wavefront ramp amortises with lanes: 64 -> 69 k, 256 -> 87 k pictures/s)")
     ap.add_argument("--staged", type=int, default=2, help="distinct pre-staged pictures per lane (cycled)")
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--intra-pct", type=int, default=0, help="side workload: %% of intra macroblocks inside the P pictures (0 = the headline workload)")

@@ -6,9 +6,10 @@
 // and the inter branch of p264_macroblock_decode (decoder/macroblock.c:832-890).
 //
 // v3 work decomposition (v1/v2 were ALU-issue bound on per-thread bookkeeping, not on filter math):
-//  * a CTA owns a tile of 8x4 macroblocks (128x64 luma samples) of one lane; the 32 macroblock
-//    records are staged in shared memory once (coalesced 16-byte loads);
-//  * the tile's 512 luma 4x4 blocks are bucketed by interpolation class (copy / H / V / diagonal /
+//  * a CTA owns a tile of 8x8 macroblocks (128x128 luma samples) of one lane; the 64 macroblock
+//    records are staged in shared memory once (coalesced 16-byte loads).  (8x4 tiles / 256 threads: 1.72 ms at 256
+//    lanes, 8x2 / 128: 1.91 ms, 8x8 / 512: 1.62 ms -- the class buckets fill their warps better the more blocks a tile has);
+//  * the tile's 1024 luma 4x4 blocks are bucketed by interpolation class (copy / H / V / diagonal /
 //    centre+b / centre+h) with shared-memory counters, so a warp runs ONE
 //    class-specialised, straight-line filter body (template parameter, no per-thread selects);
 //  * predictions go to a shared-memory picture tile; blocks that carry residual are compacted into a
@@ -22,9 +23,9 @@
 
 namespace p264b200 {
 
-constexpr int kTileW = 8, kTileH = 4;          // macroblocks per CTA tile
+constexpr int kTileW = 8, kTileH = 8;          // macroblocks per CTA tile
 constexpr int kTileMbs = kTileW * kTileH;
-constexpr int kInterThreads = 256;
+constexpr int kInterThreads = 512;
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 {
@@ -321,7 +322,7 @@ struct InterSmem {
     int nres[2];                                    // full / DC-only residual blocks
 };
 
-__global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x, int dbg)
+__global__ void __launch_bounds__(kInterThreads, 3) recon_inter_kernel(const FrameDesc *__restrict__ descs, Geometry g, int tiles_x, int dbg)
 {
     // dbg (engine knob P264B200_DBG, timing experiments only -- the pictures are wrong when set): bit 0 no luma prediction,
     // bit 1 no chroma prediction (bit 3 / 4: only without the per-cell / one-MV chroma blocks: 0.15 / 0.16 ms), bit 2 no residual.  Round 1 at 256 lanes: all 1.72 ms, no luma 0.86, no chroma 1.38, no
@@ -339,16 +340,18 @@ __global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const Fra
         uint4 v = make_uint4(0, 0, 0, 0);
         if (mbx < g.mb_w && mby < g.mb_h) v = __ldg(reinterpret_cast<const uint4 *>(fd.mbs + (size_t)mby * g.mb_w + mbx0) + rest);
         reinterpret_cast<uint4 *>(sm.mb)[tid] = v;
-    } else if (tid < kTileMbs * 6 + 3 * kMaxRefs) {
-        const int k = tid - kTileMbs * 6, r = k / 3;
-        sm.ref[r][k - 3 * r] = r < fd.num_ref ? fd.ref[r][k - 3 * r] : nullptr;
-    } else if (tid < kTileMbs * 6 + 3 * kMaxRefs + 8) {
-        sm.cnt[tid - (kTileMbs * 6 + 3 * kMaxRefs)] = 0;
-        if (tid == kTileMbs * 6 + 3 * kMaxRefs) sm.nres[0] = sm.nres[1] = 0;
+    }
+    static_assert(kTileMbs * 6 <= kInterThreads && 3 * kMaxRefs + 8 <= kInterThreads, "staging assumes one pass");
+    if (tid < 3 * kMaxRefs) {
+        const int r = tid / 3;
+        sm.ref[r][tid - 3 * r] = r < fd.num_ref ? fd.ref[r][tid - 3 * r] : nullptr;
+    } else if (tid < 3 * kMaxRefs + 8) {
+        sm.cnt[tid - 3 * kMaxRefs] = 0;
+        if (tid == 3 * kMaxRefs) sm.nres[0] = sm.nres[1] = 0;
     }
     __syncthreads();
 
-    // ---- bucket the 512 luma blocks by interpolation class and the 256 chroma blocks by "one MV for the whole
+    // ---- bucket the luma blocks by interpolation class and the chroma blocks by "one MV for the whole
     // quadrant"; list the blocks that carry residual.  Shared-memory atomics: one instruction per block.
     int my_key[2], my_pos[2];
 #pragma unroll
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kInterThreads, 6) recon_inter_kernel(const Fra
     for (int rd = 0; rd < 2; rd++) {
         const int idx = tid + kInterThreads * rd;
         if (idx >= n_items || (dbg & 1)) break;
-        const int e = sm.perm[idx], cls = e >> 12, k = e & 511;
+        const int e = sm.perm[idx], cls = e >> 12, k = e & (16 * kTileMbs - 1);
         const int mb = k >> 4, b = k & 15, bx = b & 3, by = b >> 2;
         const p264b200_mb &m = sm.mb[mb];
         const int lx = 16 * (mb & (kTileW - 1)) + 4 * bx, ly = 16 * (mb / kTileW) + 4 * by;  // position inside the tile
