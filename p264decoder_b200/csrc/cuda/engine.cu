@@ -50,8 +50,8 @@ struct p264b200_engine {
     std::vector<cudaEvent_t> ev_recon;             // [step] reconstruction that consumed that slot
     std::vector<cudaEvent_t> ev_d2h_slot;          // [frame slot] last download of that ring slot (any lane)
     cudaEvent_t ev_compute = nullptr;              // last reconstruction issued
-    std::vector<uint32_t> step_dst_mask;           // [step] ring slots written by that step
-    std::vector<uint8_t> staged_dirty, d2h_dirty;  // event recorded since creation?
+    std::vector<uint8_t> slot_dst;                 // [step][lane] ring slot that picture is reconstructed into
+    std::vector<uint8_t> desc_queued;              // [step][lane] an upload from the pinned h_descs entry may still be queued on s_h2d
     bool h2d_busy = false, d2h_busy = false;
     // frame store
     uint8_t *d_y = nullptr, *d_c = nullptr;
@@ -295,9 +295,8 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     for (auto *vec : {&e->ev_staged, &e->ev_recon, &e->ev_d2h_slot})
         for (auto &ev : *vec)
             if (!rc && (err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
-    e->step_dst_mask.assign(cfg->stage_steps, 0);
-    e->staged_dirty.assign(cfg->stage_steps, 0);
-    e->d2h_dirty.assign(cfg->n_slots, 0);
+    e->slot_dst.assign(slots, 0);
+    e->desc_queued.assign(slots, 0);
     if (!rc && (err = cudaEventCreate(&e->ev0)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreate(&e->ev1)) != cudaSuccess) fail("event", err);
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
@@ -359,6 +358,16 @@ int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_sy
         if (h.ref_slot[i] < 0 || h.ref_slot[i] >= e->cfg.n_slots) return P264B200_EINVAL;
     const size_t n_mb = (size_t)g.mb_w * g.mb_h;
     const size_t s = (size_t)step * e->cfg.lanes + lane;
+    if (e->desc_queued[s]) {
+        // The pinned descriptor is the source of an asynchronous copy that may not have run yet (a caller may stage a
+        // step again as soon as the previous call returned): wait for this step's uploads before rewriting it.  One
+        // wait per step and generation -- it also covers every other lane's entry of the step.
+        if (cudaEventSynchronize(e->ev_staged[step]) != cudaSuccess) {
+            set_err("cudaEventSynchronize(ev_staged)", cudaGetLastError());
+            return P264B200_ECUDA;
+        }
+        memset(&e->desc_queued[(size_t)step * e->cfg.lanes], 0, e->cfg.lanes);
+    }
     FrameDesc &d = e->h_descs[s];
     memset(&d, 0, sizeof(d));
     d.mbs = e->d_mbs + s * n_mb;
@@ -378,8 +387,7 @@ int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_sy
     d.num_ref = h.num_ref;
     e->slot_nintra[s] = h.n_intra;
     e->slot_flags[s] = (uint8_t)((h.n_intra > 0) | ((h.deblock != 0) << 1) | ((h.slice_type == P264B200_SLICE_P) << 2));
-    if (lane == 0) e->step_dst_mask[step] = 0;
-    e->step_dst_mask[step] |= 1u << h.dst_slot;
+    e->slot_dst[s] = (uint8_t)h.dst_slot;
     return P264B200_OK;
 }
 }  // namespace
@@ -400,6 +408,7 @@ int p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200_
     if (fs->hdr.n_coef)
         CK(cudaMemcpyAsync(e->d_coefs + s * e->coef_cap, fs->coefs, (size_t)fs->hdr.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
     CK(cudaMemcpyAsync(e->d_descs + s, &e->h_descs[s], sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
+    e->desc_queued[s] = 1;
     CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
     e->h2d_busy = true;
     return P264B200_OK;
@@ -445,6 +454,7 @@ int p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_fr
                                    e->s_h2d));
     }
     CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
+    memset(&e->desc_queued[s0], 1, n);
     CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
     e->h2d_busy = true;
     return P264B200_OK;
@@ -461,10 +471,12 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
     // G > 1: the group streams run ahead of each other ACROSS steps (no per-step barrier): a group waits for the staging
     // copy of this step, for the downloads of the slots it overwrites and for its own previous picture, nothing else --
     // so one group's deblock wavefront (ALU / latency bound) shares the SMs with the other group's recon_inter (L1 bound)
+    uint32_t dst_mask = 0;   // ring slots this step overwrites: their last downloads must have read them
+    for (int l = 0; l < n_lanes; l++) dst_mask |= 1u << e->slot_dst[(size_t)step * e->cfg.lanes + l];
     auto wait_inputs = [&](cudaStream_t st) -> cudaError_t {
         cudaError_t err = cudaStreamWaitEvent(st, e->ev_staged[step], 0);
         for (int sl = 0; sl < e->cfg.n_slots && err == cudaSuccess; sl++)
-            if (e->step_dst_mask[step] >> sl & 1) err = cudaStreamWaitEvent(st, e->ev_d2h_slot[sl], 0);
+            if (dst_mask >> sl & 1) err = cudaStreamWaitEvent(st, e->ev_d2h_slot[sl], 0);
         return err;
     };
     if (G == 1) {
@@ -563,6 +575,7 @@ int p264b200_frame_upload(p264b200_engine *e, int lane, int slot, const uint8_t 
     border_kernel<<<dim3((words + 255) / 256, 1), 256, 0, e->stream>>>(nullptr, g, e->plane(lane, slot, 0), e->plane(lane, slot, 1),
                                                                       e->plane(lane, slot, 2));
     CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev_compute, e->stream));   // downloads (s_d2h) order themselves after this upload
     return P264B200_OK;
 }
 

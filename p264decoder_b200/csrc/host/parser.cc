@@ -85,16 +85,22 @@ int Parser::read_sps(BitReader &br)
     int id = br.ue();
     if (br.eof() || id < 0 || id >= 32) return P264B200_EBITSTREAM;
     s.id = id;
-    s.log2_max_frame_num = br.ue() + 4;
+    // ue() returns -1 (or a huge value) on a damaged code: every field is range-checked before it sizes a shift or a loop
+    const int l2fn = br.ue();
+    if (l2fn < 0 || l2fn > 12) return P264B200_EBITSTREAM;
+    s.log2_max_frame_num = l2fn + 4;
     s.poc_type = br.ue();
-    if (s.poc_type == 0)
-        s.log2_max_poc_lsb = br.ue() + 4;
-    else if (s.poc_type == 1) {
+    if (s.poc_type < 0) return P264B200_EBITSTREAM;
+    if (s.poc_type == 0) {
+        const int l2poc = br.ue();
+        if (l2poc < 0 || l2poc > 12) return P264B200_EBITSTREAM;
+        s.log2_max_poc_lsb = l2poc + 4;
+    } else if (s.poc_type == 1) {
         s.delta_pic_order_always_zero = br.read1();
         br.se();
         br.se();
         int n = br.ue();
-        if (n > 256) n = 256;
+        if (n < 0 || n > 255) return P264B200_EBITSTREAM;
         for (int i = 0; i < n; i++) br.se();
     } else if (s.poc_type > 2) {
         sps_[id].id = -1;
@@ -108,7 +114,10 @@ int Parser::read_sps(BitReader &br)
     if (!s.frame_mbs_only) br.read1();
     br.read1();  // direct_8x8_inference
     if (br.read1()) {
-        for (int i = 0; i < 4; i++) s.crop[i] = br.ue();
+        for (int i = 0; i < 4; i++) {
+            s.crop[i] = br.ue();
+            if (s.crop[i] < 0) return P264B200_EBITSTREAM;
+        }
     }
     br.read1();  // vui_parameters_present: skipped like decoder/set.c:136-144
     if (br.eof()) {
@@ -147,6 +156,10 @@ int Parser::read_pps(BitReader &br)
     p.cabac = br.read1();
     p.pic_order = br.read1();
     p.num_slice_groups = br.ue() + 1;
+    if (p.num_slice_groups < 1 || p.num_slice_groups > 8) {
+        pps_[id].id = -1;
+        return P264B200_EBITSTREAM;
+    }
     if (p.num_slice_groups > 1) {
         fprintf(stderr, "FMO unsupported\n ");
         p.slice_group_map_type = br.ue();
@@ -166,6 +179,10 @@ int Parser::read_pps(BitReader &br)
     }
     p.num_ref_idx_l0 = br.ue() + 1;
     p.num_ref_idx_l1 = br.ue() + 1;
+    if (p.num_ref_idx_l0 < 1 || p.num_ref_idx_l0 > 32 || p.num_ref_idx_l1 < 1 || p.num_ref_idx_l1 > 32) {
+        pps_[id].id = -1;
+        return P264B200_EBITSTREAM;
+    }
     p.weighted_pred = br.read1();
     p.weighted_bipred = br.read(2);
     p.pic_init_qp = br.se() + 26;
@@ -290,13 +307,13 @@ int Parser::slice_header(BitReader &br, int nal_type, int nal_ref_idc, SliceHead
         ring_n_ != sps->num_ref_frames + 1) {
         asps_ = sps;
         apps_ = pps;
-        context_init();
+        if (context_init()) return P264B200_ENOMEM;
     }
     return 0;
 }
 
 // decoder/decoder.c:304-343
-void Parser::context_init()
+int Parser::context_init()
 {
     mb_w_ = asps_->mb_w;
     mb_h_ = asps_->mb_h;
@@ -305,7 +322,8 @@ void Parser::context_init()
     if (n > mbs_cap_) {
         if (mbs_) free_(mbs_);
         mbs_ = (p264b200_mb *)alloc_(n * sizeof(p264b200_mb));
-        mbs_cap_ = n;
+        mbs_cap_ = mbs_ ? n : 0;
+        if (!mbs_) return P264B200_ENOMEM;
     }
     ring_n_ = asps_->num_ref_frames + 1;
     ring_.assign(ring_n_, RingEntry{0, 0, -1, 0});
@@ -318,19 +336,22 @@ void Parser::context_init()
     ref4_.assign(n * 16, -2);
     mv4_.assign(n * 32, 0);
     geometry_changed_ = true;
+    return 0;
 }
 
-void Parser::ensure_coef(size_t need)
+int Parser::ensure_coef(size_t need)
 {
-    if (need <= coef_cap_) return;
+    if (need <= coef_cap_) return 0;
     size_t cap = std::max(need, coef_cap_ ? coef_cap_ * 2 : (size_t)mb_w_ * mb_h_ * 64 + 4096);
     int16_t *p = (int16_t *)alloc_(cap * sizeof(int16_t));
+    if (!p) return P264B200_ENOMEM;
     if (coefs_) {
         memcpy(p, coefs_, coef_n_ * sizeof(int16_t));
         free_(coefs_);
     }
     coefs_ = p;
     coef_cap_ = cap;
+    return 0;
 }
 
 // decoder/lists.c:72-143: list 0 = short-term references by descending PicNum, then long-term
@@ -639,7 +660,7 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
         }
 
     // pack (layout documented in include/p264b200_recon.h)
-    ensure_coef(coef_n_ + 16 + 16 * 16 + 8 + 8 * 16);
+    if (ensure_coef(coef_n_ + 16 + 16 * 16 + 8 + 8 * 16)) return P264B200_ENOMEM;
     m.coef_off = (uint32_t)coef_n_;
     int16_t *o = coefs_ + coef_n_;
     if (i16) {

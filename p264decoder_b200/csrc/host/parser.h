@@ -76,7 +76,7 @@ private:
     int slice(int nal_type, int nal_ref_idc, BitReader &br, p264b200_frame_syntax *out, int *got_frame);
     int slice_header(BitReader &br, int nal_type, int nal_ref_idc, SliceHeader &sh);
     int slice_data(BitReader &br, const SliceHeader &sh);
-    void context_init();
+    int context_init();
     void lists_init(const SliceHeader &sh);
     void marking(int nal_type, const SliceHeader &sh);
 
@@ -93,7 +93,7 @@ private:
     int predict_nnz(const uint8_t *grid, int stride, int x, int y) const;
     void fill_motion(p264b200_mb &m, int mbx, int mby, int bx, int by, int w, int h, int ref, int mvx, int mvy);
 
-    void ensure_coef(size_t need);
+    int ensure_coef(size_t need);
 
     alloc_fn alloc_;
     free_fn free_;
