@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--staged", type=int, default=2, help="distinct pre-staged pictures per lane (cycled)")
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--intra-pct", type=int, default=0, help="side workload: %% of intra macroblocks inside the P pictures (0 = the headline workload)")
+    ap.add_argument("--pics-per-step", type=int, default=24, help="consecutive pictures of every lane per timed step (device-resident leg): "
+                    "20 steps x 24 pictures x 256 lanes keep the timed region above one second")
+    ap.add_argument("--e2e-pics-per-step", type=int, default=4, help="pictures of every lane per step of the end-to-end leg (PCIe-bound, ~16 ms per picture of 256 lanes)")
+    ap.add_argument("--check-lanes", type=int, default=8, help="lanes whose reference rings are byte-compared with the oracle after the timed loops (0 = no parity gate)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 4K / single-lane sub-runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-parts", default="hcd", help="debug: which legs the e2e step runs (h = H2D, c = compute, d = D2H)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -201,6 +206,11 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     n = args.cpu_frames or max(8, auto_cpu_frames(args.size) // 4)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _oracle as O
+
+    if O.have_ref():
+        O.ref()          # dlopen oracle/_ref/libp264ref.so in this process too (the workers are forked from it)
     vals = []
     for i in range(args.warmup + args.steps):
         fps, kind, secs = cpu_reference(args, n, cores)
@@ -263,6 +273,190 @@ def pinned_array(lib, nbytes, dtype):
     return np.frombuffer(buf, dtype=dtype), p
 
 
+def pick_check_lanes(L, n):
+    """first / last lane, both sides of a deblock stream-quad boundary, and lanes spread over the ticket waves
+    (tickets are row-group-major over the stream quads, so distant lanes are served by different waves of CTAs)"""
+    cand = [0, L - 1, 3, 4, L // 2 - 1, L // 4 + 1, 3 * L // 4 + 2, L // 2 + 2, L // 8 + 3, 5 * L // 8 + 1, 7 * L // 8, 3 * L // 8 + 2]
+    out = []
+    for c in cand:
+        c = min(max(c, 0), L - 1)
+        if c not in out:
+            out.append(c)
+    return sorted(out[:max(0, n)])
+
+
+def _replay_worker(job):
+    """Test-infrastructure leg of the bench (the checker, never the thing measured): replays one lane's picture
+    sequence with the CPU oracle and returns the ring (all slots, tight I420 bytes) at the requested picture counts."""
+    mb_w, mb_h, n_slots, seeds, frames, checkpoints = job
+    sys.path.insert(0, str(ROOT / "tests"))
+    import p264decoder_b200 as P
+    import _oracle as O
+
+    ring = O.OracleFrames(mb_w, mb_h, n_slots)
+    for s, seed in enumerate(seeds):
+        ring.set(s, *P.smooth_picture(16 * mb_w, 16 * mb_h, seed=seed))
+    objs = []
+    for hdr_b, mbs_b, coefs_b in frames:
+        hdr = P.FrameHdr.from_buffer_copy(hdr_b)
+        objs.append(P.Frame(hdr, np.frombuffer(mbs_b, dtype=P.MB_DTYPE).copy(), np.frombuffer(coefs_b, dtype=np.int16).copy()))
+    out, done = [], 0
+    for cp in checkpoints:
+        while done < cp:
+            ring.recon(objs[done % len(objs)])
+            done += 1
+        out.append([b"".join(np.ascontiguousarray(p).tobytes() for p in fr) for fr in ring.frames])
+    return out
+
+
+class Workload:
+    """One engine with `lanes` synthetic streams of one size, T pictures per lane pre-staged in HBM and mirrored in
+    pinned host memory (the e2e leg copies straight from it)."""
+
+    def __init__(self, args, size, lanes, refs, staged, rank, local_rank, check_lanes):
+        import p264decoder_b200 as P
+
+        self.P, self.lib = P, P.load_library()
+        lib = self.lib
+        self.size, self.L, self.refs, self.rank = size, lanes, refs, rank
+        self.mb_w, self.mb_h = SIZES[size]
+        mb_w, mb_h, L = self.mb_w, self.mb_h, lanes
+        n_mb = self.n_mb = mb_w * mb_h
+        self.n_slots = n_slots = refs + 1
+        T = staged
+        if T % n_slots:
+            T += n_slots - T % n_slots          # cycling the staged pictures must keep the ring consistent
+        self.T = T
+        self.check = pick_check_lanes(L, check_lanes)
+        self.check_frames = {l: [] for l in self.check}
+        kw = dict(synth_kwargs(args, 0, rank), n_refs=refs)
+        syns = [P.Synth(mb_w, mb_h, **dict(kw, seed=stream_seed(rank, l))) for l in range(L)]
+        mbs_host, self._p1 = pinned_array(lib, T * L * n_mb * 96, np.uint8)
+        hdrs = [[None] * L for _ in range(T)]
+        coef_tmp, max_coef, total_coef = {}, 0, 0
+        for t in range(T):
+            for l in range(L):
+                fr = syns[l].next()
+                coef_tmp[(t, l)] = fr.coefs
+                max_coef = max(max_coef, len(fr.coefs))
+                total_coef += len(fr.coefs)
+                off = (t * L + l) * n_mb * 96
+                mbs_host[off : off + n_mb * 96] = fr.mbs.view(np.uint8)
+                hdrs[t][l] = fr.hdr
+                if l in self.check_frames:
+                    self.check_frames[l].append((bytes(fr.hdr), fr.mbs.tobytes(), fr.coefs.tobytes()))
+        self.coef_cap = coef_cap = (max_coef + 63) & ~63
+        coefs_host, self._p2 = pinned_array(lib, T * L * coef_cap * 2, np.int16)
+        self.fss = fss = [[None] * L for _ in range(T)]
+        for t in range(T):
+            for l in range(L):
+                c = coef_tmp[(t, l)]
+                off = (t * L + l) * coef_cap
+                coefs_host[off : off + len(c)] = c
+                fs = P.FrameSyntax()
+                fs.hdr = hdrs[t][l]
+                fs.mbs = mbs_host.ctypes.data + (t * L + l) * n_mb * 96
+                fs.coefs = coefs_host.ctypes.data + off * 2
+                fss[t][l] = fs
+        del coef_tmp
+        self.coef_slots_per_step = total_coef / T      # int16 slots per picture of every lane
+        # the batched stage call copies the records, the coefficient area up to the last lane's end and the descriptors
+        self.h2d_per_pic = L * n_mb * 96 + 2 * ((L - 1) * coef_cap + self.coef_slots_per_step / L) + L * 440
+        self.d2h_per_pic = L * (16 * mb_w * 16 * mb_h * 3 // 2)
+        self.eng = eng = P.Engine(mb_w, mb_h, n_slots=n_slots, lanes=L, stage_steps=T, coef_capacity=coef_cap, device=local_rank)
+        self.pic_seeds = [rank * 1000 + i for i in range(4)]
+        pics = [P.smooth_picture(16 * mb_w, 16 * mb_h, seed=s) for s in self.pic_seeds]
+        for l in range(L):
+            for s in range(n_slots):
+                eng.upload(l, s, *pics[(l * n_slots + s) % len(pics)])
+        for t in range(T):
+            for l in range(L):
+                eng.stage(t, l, fss[t][l])
+        eng.sync()
+        self.pic = 0                                     # pictures reconstructed per lane so far
+        self.fs_arrays = [(P.FrameSyntax * L)(*fss[t]) for t in range(T)]
+        self.slot_arrays = [(C.c_int32 * L)(*[fss[t][l].hdr.dst_slot for l in range(L)]) for t in range(T)]
+        self.out_host = None
+
+    # one picture of every lane, syntax already resident in HBM
+    def recon(self):
+        self.eng.recon_step(self.pic % self.T, self.L)
+        self.pic += 1
+
+    # one picture of every lane through the C-ABI with host buffers
+    def e2e_picture(self, parts="hcd"):
+        lib, eng, t, L = self.lib, self.eng, self.pic % self.T, self.L
+        if self.out_host is None:
+            W, H = 16 * self.mb_w, 16 * self.mb_h
+            self.fsz = W * H * 3 // 2
+            self.out_host, self._p3 = pinned_array(lib, L * self.fsz, np.uint8)
+        rc = 0
+        if "h" in parts:
+            rc |= lib.p264b200_stage_frames(eng._e, t, L, self.fs_arrays[t])        # H2D of this picture's inputs (pinned)
+        if "c" in parts:
+            rc |= lib.p264b200_recon_step(eng._e, t, L)
+        if "d" in parts:
+            rc |= lib.p264b200_frames_download(eng._e, L, self.slot_arrays[t], self.out_host.ctypes.data, self.fsz)  # D2H of every picture
+        if rc:
+            raise RuntimeError(lib.p264b200_last_error().decode())
+        self.pic += 1
+
+    def ring_bytes(self, lane):
+        return [b"".join(np.ascontiguousarray(p).tobytes() for p in self.eng.download(lane, s)) for s in range(self.n_slots)]
+
+    def replay_jobs(self, lanes, checkpoints):
+        n = self.n_slots
+        return [(self.mb_w, self.mb_h, n, [self.pic_seeds[(l * n + s) % len(self.pic_seeds)] for s in range(n)], self.check_frames[l], list(checkpoints))
+                for l in lanes]
+
+    def close(self):
+        self.eng.close()
+        for p in (self._p1, self._p2, getattr(self, "_p3", None)):
+            if p:
+                self.lib.p264b200_host_free(p)
+
+
+def run_replays(jobs):
+    import multiprocessing as mp
+
+    if not jobs:
+        return []
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        return pool.map(_replay_worker, jobs)
+
+
+def timed_device_leg(wl, warmup, steps, K):
+    """`steps` timed steps of K pictures per lane (syntax resident in HBM); returns (ms, launches, per-kernel profile, window)"""
+    eng = wl.eng
+    for _ in range(warmup * K):
+        wl.recon()
+    eng.sync()
+    eng.profile_enable(True)
+    l0 = eng.launches
+    t0 = time.time()
+    eng.timer_start()
+    for _ in range(steps * K):
+        wl.recon()
+    ms = eng.timer_stop()
+    t1 = time.time()
+    eng.sync()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    return ms, eng.launches - l0, prof, (t0, t1)
+
+
+def kernel_table(prof, ms_total, alg):
+    kernels = {}
+    for k, (kms, kn) in prof.items():
+        if kn:
+            avg = kms / kn
+            kernels[k] = {"avg_ms": avg, "launches": int(kn), "share": kms / ms_total if ms_total else None}
+            if k in alg:
+                kernels[k]["alg_bytes_per_launch"] = alg[k]
+                kernels[k]["achieved_gbs"] = alg[k] / (avg * 1e-3) / 1e9
+    return kernels
+
+
 def run_b200(args, rank, world, local_rank):
     import p264decoder_b200 as P
 
@@ -279,52 +473,9 @@ def run_b200(args, rank, world, local_rank):
         dist = dist_
     mb_w, mb_h = SIZES[args.size]
     n_mb = mb_w * mb_h
-    L, T = args.lanes, args.staged
-    if T % (args.refs + 1):
-        T += (args.refs + 1) - T % (args.refs + 1)  # cycling the staged pictures must keep the ring consistent
-    n_slots = args.refs + 1
-
-    # ---- generate the workload on the host (pinned, so the e2e leg copies straight from it)
-    syns = [P.Synth(mb_w, mb_h, **synth_kwargs(args, l, rank)) for l in range(L)]
-    mbs_host, _p1 = pinned_array(lib, T * L * n_mb * 96, np.uint8)
-    staged = [[None] * L for _ in range(T)]
-    coef_tmp, max_coef, total_coef = {}, 0, 0
-    for t in range(T):
-        for l in range(L):
-            fr = syns[l].next()
-            coef_tmp[(t, l)] = fr.coefs
-            max_coef = max(max_coef, len(fr.coefs))
-            total_coef += len(fr.coefs)
-            off = (t * L + l) * n_mb * 96
-            mbs_host[off : off + n_mb * 96] = fr.mbs.view(np.uint8)
-            staged[t][l] = fr.hdr
-    coef_cap = (max_coef + 63) & ~63
-    coefs_host, _p2 = pinned_array(lib, T * L * coef_cap * 2, np.int16)
-    fss = [[None] * L for _ in range(T)]
-    for t in range(T):
-        for l in range(L):
-            c = coef_tmp[(t, l)]
-            off = (t * L + l) * coef_cap
-            coefs_host[off : off + len(c)] = c
-            fs = P.FrameSyntax()
-            fs.hdr = staged[t][l]
-            fs.mbs = mbs_host.ctypes.data + (t * L + l) * n_mb * 96
-            fs.coefs = coefs_host.ctypes.data + off * 2
-            fss[t][l] = fs
-    del coef_tmp
-    coef_slots_per_step = total_coef / T            # int16 slots per step over all lanes
-    # the batched stage call copies the records, the coefficient area up to the last lane's end and the descriptors
-    h2d_per_step = L * n_mb * 96 + 2 * ((L - 1) * coef_cap + coef_slots_per_step / L) + L * 440
-
-    eng = P.Engine(mb_w, mb_h, n_slots=n_slots, lanes=L, stage_steps=T, coef_capacity=coef_cap, device=local_rank)
-    pics = [P.smooth_picture(16 * mb_w, 16 * mb_h, seed=rank * 1000 + i) for i in range(4)]
-    for l in range(L):
-        for s in range(n_slots):
-            eng.upload(l, s, *pics[(l * n_slots + s) % len(pics)])
-    for t in range(T):
-        for l in range(L):
-            eng.stage(t, l, fss[t][l])
-    eng.sync()
+    L, K, Ke = args.lanes, max(1, args.pics_per_step), max(1, args.e2e_pics_per_step)
+    wl = Workload(args, args.size, L, args.refs, args.staged, rank, local_rank, args.check_lanes)
+    eng = wl.eng
 
     def barrier():
         eng.sync()
@@ -332,95 +483,88 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- device-resident leg: `value`
-    for i in range(args.warmup):
-        eng.recon_step(i % T, L)
     barrier()
-    eng.profile_enable(True)
-    launches0 = eng.launches
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_wall0 = time.time()
-    eng.timer_start()
-    for i in range(args.steps):
-        eng.recon_step((args.warmup + i) % T, L)
-    ms = eng.timer_stop()
-    t_wall1 = time.time()
+    ms, launches, prof, win = timed_device_leg(wl, args.warmup, args.steps, K)
     barrier()
-    launches = eng.launches - launches0
-    prof = eng.profile_read()
-    eng.profile_enable(False)
-    clock_windows = [(t_wall0, t_wall1)]
+    clock_windows = [win]
+    pics_after_device = wl.pic
+    dev_rings = {l: wl.ring_bytes(l) for l in wl.check}          # downloaded after the timed loop, compared below
 
     # ---- end-to-end leg through the C-ABI with host buffers
-    e2e_ms, d2h_per_step = None, L * (16 * mb_w * 16 * mb_h * 3 // 2)
+    e2e_ms, e2e_lanes, e2e_rings, e2e_last = None, [], {}, {}
     if not args.no_e2e:
-        W, H = 16 * mb_w, 16 * mb_h
-        out_host, _p3 = pinned_array(lib, L * W * H * 3 // 2, np.uint8)
-        yo, uo, vo = 0, W * H, W * H + W * H // 4
-        fsz = W * H * 3 // 2
-        base = out_host.ctypes.data
-
-        fs_arrays, slot_arrays = [], []
-        for t in range(T):
-            arr = (P.FrameSyntax * L)(*fss[t])
-            fs_arrays.append(arr)
-            slot_arrays.append((C.c_int32 * L)(*[fss[t][l].hdr.dst_slot for l in range(L)]))
-
-        def e2e_step(i):
-            t = i % T
-            rc = 0
-            if "h" in args.e2e_parts:
-                rc |= lib.p264b200_stage_frames(eng._e, t, L, fs_arrays[t])        # H2D of this step's inputs (pinned)
-            if "c" in args.e2e_parts:
-                rc |= lib.p264b200_recon_step(eng._e, t, L)
-            if "d" in args.e2e_parts:
-                rc |= lib.p264b200_frames_download(eng._e, L, slot_arrays[t], base, fsz)  # D2H of every picture
-            if rc:
-                raise RuntimeError(lib.p264b200_last_error().decode())
-
-        for i in range(args.warmup):
-            e2e_step(i)
+        for _ in range(args.warmup * Ke):
+            wl.e2e_picture(args.e2e_parts)
         barrier()
         t_e0 = time.time()
         eng.timer_start()
-        n_e2e = args.steps
-        for i in range(n_e2e):
-            e2e_step(args.warmup + i)
+        for _ in range(args.steps * Ke):
+            wl.e2e_picture(args.e2e_parts)
         e2e_total = eng.timer_stop()
         clock_windows.append((t_e0, time.time()))
         barrier()
-        e2e_ms = e2e_total / n_e2e
-        assert "d" not in args.e2e_parts or int(out_host[:W].astype(np.int64).sum()) > 0
+        e2e_ms = e2e_total / args.steps
+        assert "d" not in args.e2e_parts or int(wl.out_host[: 16 * mb_w].astype(np.int64).sum()) > 0
+        if args.e2e_parts == "hcd":
+            e2e_lanes = wl.check[:1] + wl.check[-1:] if len(wl.check) > 1 else wl.check
+            e2e_rings = {l: wl.ring_bytes(l) for l in e2e_lanes}
+            e2e_last = {l: wl.out_host[l * wl.fsz : (l + 1) * wl.fsz].tobytes() for l in e2e_lanes}   # what the last D2H delivered
+    pics_after_e2e = wl.pic
 
     # ---- max over ranks
     ms_step = ms / args.steps
     ms_step, e2e_max = reduce_max([ms_step, e2e_ms or 0.0], dist, "cuda")
     e2e_ms = e2e_max if e2e_ms is not None else None
     clocks = sampler.stop(clock_windows) if sampler else None
+
+    # ---- parity gate at the timed shape: the oracle replays the same picture sequences (after the timing, on the host cores)
+    parity = None
+    if wl.check:
+        jobs = wl.replay_jobs(wl.check, [pics_after_device] + ([pics_after_e2e] if e2e_lanes else []))
+        if e2e_lanes:   # only the e2e lanes need the second checkpoint
+            jobs = [j if l in e2e_lanes else j[:5] + ([pics_after_device],) for l, j in zip(wl.check, jobs)]
+        t_r0 = time.time()
+        res = run_replays(jobs)
+        bad = []
+        last_slot = wl.fss[(pics_after_e2e - 1) % wl.T][0].hdr.dst_slot
+        for l, r in zip(wl.check, res):
+            if r[0] != dev_rings[l]:
+                bad.append(f"lane {l}: reference ring after {pics_after_device} device-resident pictures differs from the oracle")
+            if l in e2e_lanes:
+                if r[1] != e2e_rings[l]:
+                    bad.append(f"lane {l}: reference ring after the end-to-end leg ({pics_after_e2e} pictures) differs from the oracle")
+                if r[1][last_slot] != e2e_last[l]:
+                    bad.append(f"lane {l}: last downloaded picture of the end-to-end leg differs from the oracle")
+        parity = {"ok": not bad, "lanes_checked": len(wl.check), "lanes": wl.check, "ring_slots_compared": wl.n_slots,
+                  "pictures_replayed_per_lane": pics_after_device, "e2e_lanes_checked": len(e2e_lanes),
+                  "e2e_pictures_replayed_per_lane": pics_after_e2e if e2e_lanes else 0,
+                  "checker": "oracle/liboracle.so (CPU restatement) replaying the timed sequences", "seconds": round(time.time() - t_r0, 1)}
+        if bad:
+            parity["mismatches"] = bad[:8]
+    ok_all = reduce_max([0.0 if (parity is None or parity["ok"]) else 1.0], dist, "cuda")[0] == 0.0
+    if parity is not None and not ok_all:
+        parity["ok"] = False
     if rank != 0:
         if dist:
             dist.destroy_process_group()
+        if not ok_all:
+            raise SystemExit(1)
         return
 
-    value = aggregate_value(world, L, ms_step)
+    value = aggregate_value(world, L * K, ms_step)
     unit = f"{args.size}_frames/s"
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    # per-kernel algorithmic bytes per launch (one launch = L pictures)
+    # per-kernel algorithmic bytes per launch (one launch = one picture of every lane = L pictures)
     alg = {
-        "recon_inter": L * n_mb * BYTES_MC_FIXED + 2.0 * coef_slots_per_step,
+        "recon_inter": L * n_mb * BYTES_MC_FIXED + 2.0 * wl.coef_slots_per_step,
         "deblock": L * n_mb * BYTES_DEBLOCK,
     }
-    kernels = {}
-    for k, (kms, kn) in prof.items():
-        if kn:
-            avg = kms / kn
-            kernels[k] = {"avg_ms": avg, "launches": int(kn), "share": kms / ms if ms else None}
-            if k in alg:
-                kernels[k]["alg_bytes_per_launch"] = alg[k]
-                kernels[k]["achieved_gbs"] = alg[k] / (avg * 1e-3) / 1e9
+    kernels = kernel_table(prof, ms, alg)
     dominant = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["avg_ms"])
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
@@ -430,23 +574,34 @@ def run_b200(args, rank, world, local_rank):
             traffic = rec and rec.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    ms_pic = ms_step / K                                  # one picture of every lane
+    pipe = (alg["recon_inter"] + alg["deblock"]) / (ms_pic * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
         "frac": kernels[dominant]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-        "alg_bytes_per_launch": alg[dominant],
-        "pipeline_achieved": (alg["recon_inter"] + alg["deblock"]) / (ms_step * 1e-3) / 1e9,
-        "pipeline_frac": (alg["recon_inter"] + alg["deblock"]) / (ms_step * 1e-3) / 1e9 / peak,
+        "alg_bytes_per_launch": alg[dominant], "pipeline_achieved": pipe, "pipeline_frac": pipe / peak,
     }
+    cfg = workload_config(args, L)
+    cfg["pictures_per_lane_per_step"] = K
     line = {
         "metric": f"reconstructed_{args.size}_frames_per_s", "value": value, "unit": unit, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, L),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_picture_of_all_lanes": ms_pic,
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
         "mpixel_per_s": value * 16 * mb_w * 16 * mb_h / 1e6,
-        "roofline": roofline, "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
     if e2e_ms is not None:
-        line["e2e"] = {"value": aggregate_value(world, L, e2e_ms), "unit": unit, "h2d_bytes_per_step": int(h2d_per_step),
-                       "d2h_bytes_per_step": int(d2h_per_step), "ms_per_step": e2e_ms}
+        line["e2e"] = {"value": aggregate_value(world, L * Ke, e2e_ms), "unit": unit, "h2d_bytes_per_step": int(wl.h2d_per_pic * Ke),
+                       "d2h_bytes_per_step": int(wl.d2h_per_pic * Ke), "ms_per_step": e2e_ms, "pictures_per_lane_per_step": Ke}
+    wl.close()
+    del wl
+
+    # ---- extras (N=1 only; short sub-runs outside the headline's timed regions): 4K / multi-reference and one-lane latency
+    if world == 1 and not args.no_extras and args.size == "1080p" and not args.intra_pct:
+        line["extra"] = run_extras(args, rank, local_rank, peak)
+        if any(isinstance(v, dict) and v.get("parity") and not v["parity"]["ok"] for v in line["extra"].values()):
+            ok_all = False
     if not args.no_cpu:
         cores = os.cpu_count() or 1
         n = args.cpu_frames or auto_cpu_frames(args.size)
@@ -460,6 +615,48 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+    if not ok_all:
+        print("bench.py: PARITY MISMATCH against the oracle -- the numbers above are void", file=sys.stderr)
+        raise SystemExit(1)
+
+
+def run_extras(args, rank, local_rank, peak):
+    """configs[3] (4K, 4 references) and the single-lane latency as short sub-runs, each with its own parity check."""
+    import copy
+
+    out = {}
+    # 4K, 4 references, 48 lanes
+    a4 = copy.copy(args)
+    a4.size, a4.refs = "4k", 4
+    L4, K4, steps4, warm4 = 48, 2, 8, 3
+    wl = Workload(a4, "4k", L4, 4, 5, rank, local_rank, 2)
+    ms, _, prof, _ = timed_device_leg(wl, warm4, steps4, K4)
+    n_mb = wl.n_mb
+    alg = {"recon_inter": L4 * n_mb * BYTES_MC_FIXED + 2.0 * wl.coef_slots_per_step, "deblock": L4 * n_mb * BYTES_DEBLOCK}
+    kt = kernel_table(prof, ms, alg)
+    ms_pic = ms / (steps4 * K4)
+    rings = {l: wl.ring_bytes(l) for l in wl.check}
+    res = run_replays(wl.replay_jobs(wl.check, [wl.pic]))
+    ok = all(r[0] == rings[l] for l, r in zip(wl.check, res))
+    pipe = (alg["recon_inter"] + alg["deblock"]) / (ms_pic * 1e-3) / 1e9
+    out["4k"] = {"workload": "BASELINE.json configs[3]: synthetic 4K (3840x2160) P streams, 4 reference frames, deblocking on", "lanes": L4,
+                 "value": L4 / (ms_pic * 1e-3), "unit": "4k_frames/s", "ms_per_picture_of_all_lanes": ms_pic,
+                 "roofline": {"kernel": "recon_inter", "frac": kt["recon_inter"]["achieved_gbs"] / peak, "achieved": kt["recon_inter"]["achieved_gbs"],
+                              "deblock_frac": kt["deblock"]["achieved_gbs"] / peak, "pipeline_frac": pipe / peak},
+                 "parity": {"ok": ok, "lanes_checked": len(wl.check), "pictures_replayed_per_lane": wl.pic}}
+    wl.close()
+    del wl
+    # one 1080p lane: the wavefront-latency floor of a single stream (SURVEY 7, hard part 1)
+    wl = Workload(args, "1080p", 1, args.refs, 2, rank, local_rank, 1)
+    ms, _, prof, _ = timed_device_leg(wl, 3, 40, 1)
+    rings = {l: wl.ring_bytes(l) for l in wl.check}
+    res = run_replays(wl.replay_jobs(wl.check, [wl.pic]))
+    ok = all(r[0] == rings[l] for l, r in zip(wl.check, res))
+    out["single_lane"] = {"workload": "one 1080p stream, one picture per launch sequence (syntax resident in HBM)", "ms_per_picture": ms / 40,
+                          "value": 1000.0 * 40 / ms, "unit": "1080p_frames/s",
+                          "kernels_ms": {k: v[0] / v[1] for k, v in prof.items() if v[1]}, "parity": {"ok": ok, "pictures_replayed_per_lane": wl.pic}}
+    wl.close()
+    return out
 
 
 def main():

@@ -1,7 +1,8 @@
 // Single-block device entry points behind the reference's function-pointer tables
 // (include/p264_b200_tables.h).  Each shim stages the caller's block (plus exactly the
 // neighbouring samples the reference routine would read) into a small device scratch tile,
-// runs the SAME device functions the batched frame kernels inline, and copies the result back.
+// runs the SAME device functions the batched frame kernels inline (for the deblocking slots: the packed
+// two-lines-per-register filters of swar.cuh, not the scalar forms), and copies the result back.
 // A test surface: one launch + two copies per call; never used by the frame path.
 #include <cuda_runtime.h>
 
@@ -263,33 +264,41 @@ __global__ void blockop_kernel(Scratch *s, int op)
         break;
     }
     case OP_DBF_LUMA:
-        if (t < 16) {
+        // the PACKED two-lines-per-register filters of swar.cuh, i.e. the instructions the frame kernel executes
+        // (VABSDIFF4 / VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.RELU): thread t filters lines 2t and 2t+1, which lie in
+        // the same 4-line segment and therefore share tc0
+        if (t < 8) {
             const int xs = a[0] == 0 ? 1 : TS, ys = a[0] == 0 ? TS : 1;
-            uint8_t *px = p + t * ys;
-            int v[8];
-            for (int k = 0; k < 8; k++) v[k] = px[(k - 4) * xs];
+            uint8_t *pa = p + (2 * t) * ys, *pb = pa + ys;
+            uint32_t v[8];
+            for (int k = 0; k < 8; k++) v[k] = (uint32_t)pa[(k - 4) * xs] | ((uint32_t)pb[(k - 4) * xs] << 16);
             if (a[3]) {
-                dbf_luma_strong(v, a[1], a[2]);
+                const swar::EdgeK k4 = swar::edge_k(a[1], a[2], 0);
+                swar::luma_strong(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], k4, a[1]);
             } else {
-                const int tc0 = a[4 + (t >> 2)];
-                if (tc0 >= 0) dbf_luma_normal(v, a[1], a[2], tc0);
+                const int tc0 = a[4 + (t >> 1)];
+                if (tc0 >= 0) {
+                    const swar::EdgeK k = swar::edge_k(a[1], a[2], tc0);
+                    swar::luma_normal(v[1], v[2], v[3], v[4], v[5], v[6], k);
+                }
             }
-            for (int k = 1; k < 7; k++) px[(k - 4) * xs] = (uint8_t)v[k];
+            for (int k = 1; k < 7; k++) pa[(k - 4) * xs] = (uint8_t)(v[k] & 0xff), pb[(k - 4) * xs] = (uint8_t)((v[k] >> 16) & 0xff);
         }
         break;
     case OP_DBF_CHROMA:
-        if (t < 8) {
+        if (t < 4) {
             const int xs = a[0] == 0 ? 1 : TS, ys = a[0] == 0 ? TS : 1;
-            uint8_t *px = p + t * ys;
-            int v[4];
-            for (int k = 0; k < 4; k++) v[k] = px[(k - 2) * xs];
-            const int tc = a[4 + (t >> 1)];
-            if (a[3])
-                dbf_chroma(v, a[1], a[2], 4, 0);
-            else if (tc > 0)
-                dbf_chroma(v, a[1], a[2], 1, tc);
-            px[-xs] = (uint8_t)v[1];
-            px[0] = (uint8_t)v[2];
+            uint8_t *pa = p + (2 * t) * ys, *pb = pa + ys;
+            uint32_t v[4];
+            for (int k = 0; k < 4; k++) v[k] = (uint32_t)pa[(k - 2) * xs] | ((uint32_t)pb[(k - 2) * xs] << 16);
+            const int tc = a[4 + t];
+            if (a[3] || tc > 0) {
+                // chroma_edge2 takes tc0 and adds the +1 of core/frame.c:351-377 itself; the table passes tc = tc0 + 1
+                const swar::EdgeK k = swar::edge_k(a[1], a[2], a[3] ? 0 : tc - 1);
+                swar::chroma_edge2(v[0], v[1], v[2], v[3], k, a[3] != 0);
+            }
+            pa[-xs] = (uint8_t)(v[1] & 0xff), pb[-xs] = (uint8_t)((v[1] >> 16) & 0xff);
+            pa[0] = (uint8_t)(v[2] & 0xff), pb[0] = (uint8_t)((v[2] >> 16) & 0xff);
         }
         break;
     case OP_SSD: {

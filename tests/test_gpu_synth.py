@@ -72,7 +72,7 @@ def test_lanes_batched():
 
 @pytest.mark.parametrize("mb_w,mb_h", [(1, 1), (2, 1), (1, 3), (3, 2), (1, 9), (9, 1), (5, 17)])
 def test_tiny_and_ragged_geometries(mb_w, mb_h):
-    # pictures smaller than one recon_inter tile (8x4 MBs), narrower than the deblock ring (4 MBs), a single
+    # pictures smaller than one recon_inter tile (8x8 MBs), narrower than the deblock ring (4 MBs), a single
     # macroblock row / column, and 17 rows = two full deblock row groups + one row
     _run_stream(mb_w, mb_h, 4, lanes=3, n_refs=2, seed=31 + mb_w * 7 + mb_h, intra_pct=15, sweep_offsets=1, mv_range=6)
 
@@ -119,6 +119,53 @@ def test_1080p_bench_shaped_many_lanes_cycled_staging():
 
 def test_4k_multiref_two_pictures():
     _run_stream(240, 135, 2, n_refs=4, seed=2160, sweep_offsets=1, first_intra=0)
+
+
+def test_4k_multiref_many_lanes():
+    """configs[3] at a batched shape: 16 lanes x 4K x 4 references, three unsynchronised steps over pre-staged syntax
+    (16 lanes x 17 row groups x 2 roles = 136 deblock CTAs, multi-reference windows from four ring slots)."""
+    mb_w, mb_h, lanes, refs, steps = 240, 135, 16, 4, 3
+    n_slots = refs + 1
+    eng = P.Engine(mb_w, mb_h, n_slots=n_slots, lanes=lanes, stage_steps=steps)
+    rings = {}
+    staged = [[None] * lanes for _ in range(steps)]
+    check = [0, 3, 4, 9, lanes - 1]
+    pics = [P.smooth_picture(16 * mb_w, 16 * mb_h, seed=s) for s in range(3)]
+    for l in range(lanes):
+        syn = P.Synth(mb_w, mb_h, n_refs=refs, seed=4000 + l, first_intra=0, sweep_offsets=1, intra_pct=1 if l == 3 else 0)
+        for s in range(n_slots):
+            eng.upload(l, s, *pics[(l + s) % 3])
+        if l in check:
+            rings[l] = O.OracleFrames(mb_w, mb_h, n_slots)
+            for s in range(n_slots):
+                rings[l].set(s, *pics[(l + s) % 3])
+        for t in range(steps):
+            staged[t][l] = syn.next()
+            eng.stage(t, l, staged[t][l].syntax())
+    for t in range(steps):
+        eng.recon_step(t, lanes)
+    eng.sync()
+    for l in check:
+        for t in range(steps):
+            rings[l].recon(staged[t][l])
+        for slot in range(n_slots):
+            _compare(eng.download(l, slot), rings[l].frames[slot], staged[0][l], f"4K lane {l} slot {slot} after {steps} steps")
+    eng.close()
+
+
+def test_randomised_stress_time_boxed():
+    """tools/stress.py for a fixed wall-clock budget: random geometries, lane counts, reference counts and stream options --
+    the check aimed at the schedule-dependent parts (tickets, mbarrier rings, progress words, class buckets)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    import stress
+
+    cases, pictures = stress.run(budget=35.0, seed=2)
+    assert cases >= 3 and pictures >= 20
+    cases, pictures = stress.run(budget=25.0, seed=3, big=True)
+    assert cases >= 1
 
 
 def test_batched_stage_and_packed_download_match_per_picture_path():

@@ -128,13 +128,25 @@ def test_deblock_tables(libs):
     ours, ref = libs
     to, tr = table(ours, "p264_deblock_init", 8, 0), table(ref, "p264_deblock_init", 8, 0)
     rng = np.random.default_rng(4)
-    for it in range(40):
+    # our slots run the PACKED s16x2 filters of swar.cuh on the device (the instructions of the frame kernel)
+    for it in range(160):
         base = rng.integers(60, 200)
         pix = np.clip(base + rng.integers(-12, 13, (40, 48)), 0, 255).astype(np.uint8)
         if it % 3 == 0:
             pix = rng.integers(0, 256, (40, 48)).astype(np.uint8)
         alpha, beta = int(rng.integers(0, 256)), int(rng.integers(0, 19))
+        if it >= 40:
+            # near-threshold lines: a step of about alpha across the edge (both directions), texture of about beta beside it,
+            # so |p0-q0| - alpha, |p1-p0| - beta, |p2-p0| - beta and |p0-q0| - ((alpha>>2)+2) all change sign inside one call
+            alpha, beta = int(rng.integers(2, 80)), int(rng.integers(1, 19))
+            step = alpha + rng.integers(-2, 3, (40, 48)) if it % 2 else (alpha >> 2) + 2 + rng.integers(-2, 3, (40, 48))
+            rr, cc = np.mgrid[0:40, 0:48]
+            tex = rng.integers(-1, 2, (40, 48)) * (beta + rng.integers(-1, 2, (40, 48))) // (1 + (it % 3))
+            lo = 0 if it % 5 else -30   # some blocks near 0 / 255 for the clip8 of p0 + delta
+            pix = np.clip(base + lo * 4 + ((rr >= 12) ^ (cc >= 12)) * step + tex, 0, 255).astype(np.uint8)
         tc = rng.integers(-1, 12, 4).astype(np.int8)
+        if it >= 100:
+            tc = rng.integers(0, 26, 4).astype(np.int8)   # tc0 table tops out at 25
         for slot in range(4):
             a, b = pix.copy(), pix.copy()
             F_DBF(tr[slot])(a.ctypes.data + 12 * 48 + 12, 48, alpha, beta, tc.ctypes.data)

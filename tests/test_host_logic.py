@@ -126,3 +126,26 @@ def test_empty_and_tiny_pictures_through_oracle():
     for _ in range(5):
         y, u, v = ring.recon(syn.next())
         assert y.shape == (16, 16)
+
+
+def test_bench_parity_gate_helpers():
+    """bench.py's parity gate (host side): lane selection and the oracle replay worker that re-derives a lane's
+    reference ring from the staged pictures, cycled the way the timed loops cycle them."""
+    import bench
+
+    lanes = bench.pick_check_lanes(256, 8)
+    assert len(lanes) == 8 and lanes[0] == 0 and lanes[-1] == 255 and 3 in lanes and 4 in lanes
+    assert bench.pick_check_lanes(1, 8) == [0] and bench.pick_check_lanes(2, 8) == [0, 1] and bench.pick_check_lanes(9, 0) == []
+    mb_w, mb_h, n_slots, T = 5, 4, 2, 2
+    syn = P.Synth(mb_w, mb_h, n_refs=1, seed=5, first_intra=0)
+    frames = [syn.next() for _ in range(T)]
+    job = (mb_w, mb_h, n_slots, [11, 12], [(bytes(f.hdr), f.mbs.tobytes(), f.coefs.tobytes()) for f in frames], [3, 6])
+    got = bench._replay_worker(job)
+    ring = O.OracleFrames(mb_w, mb_h, n_slots)
+    for s, seed in enumerate([11, 12]):
+        ring.set(s, *P.smooth_picture(16 * mb_w, 16 * mb_h, seed=seed))
+    for cp_i, cp in enumerate([3, 6]):
+        for i in range(0 if cp_i == 0 else 3, cp):
+            ring.recon(frames[i % T])
+        want = [b"".join(np.ascontiguousarray(p).tobytes() for p in fr) for fr in ring.frames]
+        assert got[cp_i] == want

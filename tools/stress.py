@@ -16,10 +16,9 @@ import p264decoder_b200 as P  # noqa: E402
 import _oracle as O  # noqa: E402
 
 
-def main():
-    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    big = len(sys.argv) > 3 and sys.argv[3] == "big"
+def run(budget=60.0, seed=1, big=False):
+    """returns (configurations, pictures) checked inside the wall-clock budget; raises AssertionError on the first mismatch"""
+    rng = np.random.default_rng(seed)
     t0, cases, pictures = time.time(), 0, 0
     while time.time() - t0 < budget:
         mb_w, mb_h = (int(rng.integers(40, 131)), int(rng.integers(20, 71))) if big else (int(rng.integers(1, 40)), int(rng.integers(1, 40)))
@@ -51,11 +50,23 @@ def main():
                 got = eng.download(l, fr.hdr.dst_slot)
                 for name, g, w in zip("YUV", got, want):
                     if not np.array_equal(g, w):
-                        print(f"MISMATCH: {mb_w}x{mb_h} MBs, {lanes} lanes, picture {i} lane {l} plane {name}, options {kw}")
-                        sys.exit(1)
+                        raise AssertionError(f"MISMATCH: {mb_w}x{mb_h} MBs, {lanes} lanes, picture {i} lane {l} plane {name}, options {kw}")
                 pictures += 1
         eng.close()
         cases += 1
+    return cases, pictures
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
+    t0 = time.time()
+    try:
+        cases, pictures = run(budget, seed, big)
+    except AssertionError as e:
+        print(e)
+        sys.exit(1)
     print(f"stress ok: {cases} random configurations, {pictures} pictures bit-exact in {time.time() - t0:.0f} s")
 
 
