@@ -72,6 +72,24 @@ int  p264b200_multi_step(p264b200_multi *m, uint8_t *produced);
 const uint8_t *p264b200_multi_picture(const p264b200_multi *m, int s, int *width, int *height);
 
 /* ------------------------------------------------------------------------- *
+ * Closed-GOP splitter + ordered merge: ONE Annex-B stream cut at its IDR pictures
+ * (decoder/decoder.c:43-64: an IDR empties the DPB, so every closed GOP decodes on its own), GOP g decoded on
+ * lane g mod L of one batched engine, pictures delivered in stream order.  Across GPUs: rank r of N opens the
+ * GOPs g with g mod N == r (p264b200_gop_scan gives the byte ranges) -- no exchange between ranks.
+ * ------------------------------------------------------------------------- */
+/* byte offset and picture count of every closed GOP (each begins at the parameter sets directly in front of its
+ * IDR slice); returns the number of GOPs in the stream, fills at most max_gops entries */
+int  p264b200_gop_scan(const uint8_t *annexb, size_t bytes, size_t *gop_begin, int32_t *gop_pictures, int max_gops);
+typedef struct p264b200_gopdec p264b200_gopdec;
+/* returns the number of lanes in use (<= lanes, <= GOPs) or a negative P264B200_E* code; the byte stream is copied */
+int  p264b200_gopdec_open(p264b200_gopdec **out, int device, int lanes, int threads, const uint8_t *annexb, size_t bytes);
+void p264b200_gopdec_close(p264b200_gopdec *d);
+int  p264b200_gopdec_gops(const p264b200_gopdec *d);
+/* next picture IN STREAM ORDER as a tight I420 image owned by the decoder (valid until the next call):
+ * 1 = delivered, 0 = end of stream, < 0 = error */
+int  p264b200_gopdec_next(p264b200_gopdec *d, const uint8_t **picture, int *width, int *height);
+
+/* ------------------------------------------------------------------------- *
  * Synthetic stream generator (BASELINE.json configs 3-5): emits FrameSyntax for a
  * stream of random P pictures (optionally after one intra picture).  Deterministic
  * for a given cfg.  Not part of the reference (which ships no generator or tests).

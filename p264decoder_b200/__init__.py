@@ -153,6 +153,11 @@ def load_library() -> C.CDLL:
         "p264b200_annexb_next": (i32, [u8p, C.c_size_t] + [C.POINTER(C.c_size_t)] * 3),
         "p264b200_nal_unescape": (i32, [u8p, i32, u8p, C.POINTER(i32), C.POINTER(i32)]),
         "p264b200_cavlc_table_entry": (i32, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "p264b200_gop_scan": (i32, [u8p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), i32]),
+        "p264b200_gopdec_open": (i32, [C.POINTER(vp), i32, i32, i32, u8p, C.c_size_t]),
+        "p264b200_gopdec_close": (None, [vp]),
+        "p264b200_gopdec_gops": (i32, [vp]),
+        "p264b200_gopdec_next": (i32, [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
         "p264b200_synth_default": (None, [C.POINTER(SynthCfg), i32, i32]),
         "p264b200_synth_open": (vp, [C.POINTER(SynthCfg)]),
         "p264b200_synth_close": (None, [vp]),
@@ -401,6 +406,35 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self._lib.p264b200_engine_stream(self._e) or 0)
+
+
+def gop_scan(data: np.ndarray, max_gops: int = 4096):
+    """[(byte offset, pictures)] of every closed GOP of an Annex-B stream (no GPU needed)."""
+    lib = load_library()
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    begin, pics = (C.c_size_t * max_gops)(), (C.c_int32 * max_gops)()
+    n = lib.p264b200_gop_scan(data.ctypes.data, len(data), begin, pics, max_gops)
+    _check(n, "p264b200_gop_scan")
+    return [(int(begin[i]), int(pics[i])) for i in range(min(n, max_gops))]
+
+
+def decode_annexb_gops(data: np.ndarray, lanes: int, device: int = 0, threads: int = 0):
+    """One Annex-B stream cut at its IDR pictures, closed GOP g decoded on lane g mod `lanes` of one batched engine;
+    yields the tight I420 pictures (one uint8 array each) in STREAM order."""
+    lib = load_library()
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    d = C.c_void_p()
+    _check(lib.p264b200_gopdec_open(C.byref(d), device, lanes, threads, data.ctypes.data, len(data)), "p264b200_gopdec_open")
+    try:
+        pic, w, h = C.c_void_p(), C.c_int(), C.c_int()
+        while True:
+            r = lib.p264b200_gopdec_next(d, C.byref(pic), C.byref(w), C.byref(h))
+            _check(r, "p264b200_gopdec_next")
+            if r == 0:
+                break
+            yield np.frombuffer(C.string_at(pic.value, w.value * h.value * 3 // 2), dtype=np.uint8), w.value, h.value
+    finally:
+        lib.p264b200_gopdec_close(d)
 
 
 def decode_annexb(data: np.ndarray, device: int = 0):

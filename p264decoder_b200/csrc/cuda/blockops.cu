@@ -172,7 +172,15 @@ __global__ void blockop_kernel(Scratch *s, int op)
     }
     case OP_MC_LUMA: {
         const int w4 = a[0] >> 2, h4 = a[1] >> 2;
-        if (t < w4 * h4) {
+        if ((h4 & 1) == 0) {
+            // partitions at least 8 rows tall: the 4x8 strip bodies of the frame kernel
+            if (t < w4 * (h4 >> 1)) {
+                const int bx = 4 * (t % w4), by = 8 * (t / w4);
+                uint32_t px[8];
+                mc_luma_4x8(p + by * TS + bx, TS, a[2], a[3], px);
+                for (int r = 0; r < 8; r++) *reinterpret_cast<uint32_t *>(q + (by + r) * TS + bx) = px[r];
+            }
+        } else if (t < w4 * h4) {
             const int bx = 4 * (t % w4), by = 4 * (t / w4);
             uint32_t px[4];
             mc_luma_4x4(p + by * TS + bx, TS, a[2], a[3], px);

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #define P264B200_DEFINE_KERNELS 1
@@ -89,6 +90,9 @@ struct p264b200_engine {
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {}, ev_hi_done[kMaxGroups] = {};
     int dbf_pad_bytes = 0;   // P264B200_DBF_PAD (KB): dynamic shared memory added to deblock CTAs = fewer of them per SM, room for recon_inter CTAs
     bool groups_dirty = false;  // group streams hold work the main stream has not joined yet
+    int inter_variant = 2;  // P264B200_INTER_VARIANT: CTA shape / register budget / tile height of recon_inter: 0 = 512 threads x 2 CTAs per SM
+                            // (64 registers), 1 = 512 x 3 (40), 2 = 384 x 3 (56, default), 3 = 256 x 4 (64); 8x16-macroblock tiles: 4 = 576 x 2 (56),
+                            // 5 = 512 x 2 (64), 6 = 768 x 1 (80)
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
     int trace_ticket = -1;  // P264B200_TRACE: deblock CTA (by ticket) whose per-step cycle marks are recorded
 
@@ -302,6 +306,17 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char *v = getenv("P264B200_INTER_VARIANT")) e->inter_variant = atoi(v);
+    {
+        const std::pair<const void *, int> kern[] = {
+            {(const void *)recon_inter_kernel<512, 2, 8>, (int)sizeof(InterSmem<8>)},   {(const void *)recon_inter_kernel<512, 3, 8>, (int)sizeof(InterSmem<8>)},
+            {(const void *)recon_inter_kernel<384, 3, 8>, (int)sizeof(InterSmem<8>)},   {(const void *)recon_inter_kernel<256, 4, 8>, (int)sizeof(InterSmem<8>)},
+            {(const void *)recon_inter_kernel<576, 2, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<512, 2, 16>, (int)sizeof(InterSmem<16>)},
+            {(const void *)recon_inter_kernel<768, 1, 16>, (int)sizeof(InterSmem<16>)}};
+        for (auto &k : kern)
+            if (!rc && (err = cudaFuncSetAttribute(k.first, cudaFuncAttributeMaxDynamicSharedMemorySize, k.second)) != cudaSuccess)
+                fail("cudaFuncSetAttribute(recon_inter)", err);
+    }
     if (const char *pad = getenv("P264B200_DBF_PAD")) e->dbf_pad_bytes = atoi(pad) * 1024;
     if (!rc && e->dbf_pad_bytes > 0 &&
         (err = cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->dbf_pad_bytes)) != cudaSuccess)
@@ -506,8 +521,17 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         int *tickets = e->d_sync + p264b200_engine::kSyncHdr * gi;
         if (pslice) {
             ProfScope p(e, K_INTER, st);
-            const int tiles_x = (g.mb_w + kTileW - 1) / kTileW, tiles_y = (g.mb_h + kTileH - 1) / kTileH;
-            recon_inter_kernel<<<dim3(tiles_x * tiles_y, nl), kInterThreads, 0, st>>>(descs, g, tiles_x, e->dbg);
+            const int th = e->inter_variant >= 4 ? 16 : 8;
+            const dim3 grid((g.mb_w + kTileW - 1) / kTileW, (g.mb_h + th - 1) / th, nl);
+            switch (e->inter_variant) {
+            case 0: recon_inter_kernel<512, 2, 8><<<grid, 512, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 1: recon_inter_kernel<512, 3, 8><<<grid, 512, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 3: recon_inter_kernel<256, 4, 8><<<grid, 256, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 4: recon_inter_kernel<576, 2, 16><<<grid, 576, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
+            case 5: recon_inter_kernel<512, 2, 16><<<grid, 512, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
+            case 6: recon_inter_kernel<768, 1, 16><<<grid, 768, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
+            default: recon_inter_kernel<384, 3, 8><<<grid, 384, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            }
         }
         if (G > 1) {
             CK(cudaEventRecord(e->ev_mc[gi], st));

@@ -78,3 +78,20 @@ def test_cli_matches_reference_md5(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "decoded total 300 frames" in r.stderr
     assert hashlib.md5(out.read_bytes()).hexdigest() == "a482adab07324894b443e081a84ee1df"
+
+
+def test_unmodified_reference_cli_relinked_against_the_engine(tmp_path):
+    """The drop-in claim end to end: the reference's OWN CLI source (p264decoder.c:164-381 + core/mdate.c, compiled
+    unmodified against its own p264.h by oracle/Makefile where /root/reference is mounted) linked against
+    libp264b200.so instead of the reference's decoder/ and core/ objects, decoding bin/f26.264 on the GPU."""
+    path = O.f26_path()
+    exe = O.REF_DIR / "p264dec_relinked"
+    if path is None or not exe.exists():
+        pytest.skip("oracle/_ref/p264dec_relinked not built (needs /root/reference at build time)")
+    ldd = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "libp264b200.so" in ldd and "libp264ref" not in ldd
+    out = tmp_path / "f26_relinked.yuv"
+    r = subprocess.run([str(exe), "-d", str(path), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert "decoded total 300 frames" in r.stderr
+    assert hashlib.md5(out.read_bytes()).hexdigest() == "a482adab07324894b443e081a84ee1df"

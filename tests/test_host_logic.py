@@ -149,3 +149,17 @@ def test_bench_parity_gate_helpers():
             ring.recon(frames[i % T])
         want = [b"".join(np.ascontiguousarray(p).tobytes() for p in fr) for fr in ring.frames]
         assert got[cp_i] == want
+
+
+def test_gop_scan_f26():
+    """closed-GOP splitter, host side: bin/f26.264 has IDR pictures at 0 and 250; every GOP must begin at
+    the parameter sets in front of its IDR slice and the picture counts must add up to the 300 frames"""
+    path = O.f26_path()
+    if path is None:
+        pytest.skip("oracle/_ref/f26.264 not built")
+    data = np.fromfile(path, dtype=np.uint8)
+    gops = P.gop_scan(data)
+    assert [n for _, n in gops] == [250, 50]
+    assert gops[0][0] == 0
+    for off, _ in gops:
+        assert bytes(data[off : off + 4]) == b"\x00\x00\x00\x01" and (data[off + 4] & 0x1f) in (6, 7)   # SEI / SPS first

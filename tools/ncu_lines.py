@@ -10,6 +10,7 @@ by instruction order inside the kernel's .text section.
 usage: ncu_lines.py REPORT.ncu-rep CUBIN KERNEL_SUBSTRING [top_n] [column]
 (column: "Instructions Executed" by default; "# Samples" gives the warp-stall samples = where the time goes)
 """
+import os
 import collections
 import csv
 import re
@@ -38,7 +39,7 @@ def main():
     lines, in_k, loc = [], False, ("?", 0)
     for l in dis:
         if l.startswith("\t.section\t.text."):
-            in_k = kname in l
+            in_k = (os.environ.get("CUBIN_KERNEL") or kname) in l
             continue
         if l.startswith("\t.section"):
             in_k = False
