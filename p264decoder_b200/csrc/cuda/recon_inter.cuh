@@ -623,20 +623,30 @@ __global__ void __launch_bounds__(THREADS, MINB) recon_inter_kernel(const FrameD
                 for (int o = 128 * q; o < 2 * n16; o += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o));
             }
             const int2 v0 = *reinterpret_cast<const int2 *>(m.mv[lb0]), v1 = *reinterpret_cast<const int2 *>(m.mv[lb0 + 4]);
+            const bool one = v0.x == v0.y && v0.x == v1.x && v0.x == v1.y;
+            if (one) {
+                // one vector for the quadrant (every partition of 8x8 and up): its two strips sit side by side in the list, so
+                // that the lanes of a 16-wide partition read the same cache lines in the same load instruction
+                const int l0 = luma_list(mc_class(v0.x & 3, (v0.x >> 16) & 3));
+                const int pos = SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 2);
+                sm.list[pos] = (uint16_t)(mb << 5 | lb0 << 1);
+                sm.list[pos + 1] = (uint16_t)(mb << 5 | (lb0 + 1) << 1);
+            } else {
 #pragma unroll
-            for (int sx = 0; sx < 2; sx++) {
-                const int top = sx ? v0.y : v0.x, bot = sx ? v1.y : v1.x;
-                const int l0 = luma_list(mc_class(top & 3, (top >> 16) & 3));
-                const int e0 = mb << 5 | (lb0 + sx) << 1;
-                if (top == bot) {
-                    sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)e0;
-                } else {
-                    const int l1 = luma_list(mc_class(bot & 3, (bot >> 16) & 3));
-                    sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)(e0 | 1);
-                    sm.list[SM::list_off(l1) + atomicAdd(&sm.cnt[l1], 1)] = (uint16_t)((e0 + (4 << 1)) | 1);
+                for (int sx = 0; sx < 2; sx++) {
+                    const int top = sx ? v0.y : v0.x, bot = sx ? v1.y : v1.x;
+                    const int l0 = luma_list(mc_class(top & 3, (top >> 16) & 3));
+                    const int e0 = mb << 5 | (lb0 + sx) << 1;
+                    if (top == bot) {
+                        sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)e0;
+                    } else {
+                        const int l1 = luma_list(mc_class(bot & 3, (bot >> 16) & 3));
+                        sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)(e0 | 1);
+                        sm.list[SM::list_off(l1) + atomicAdd(&sm.cnt[l1], 1)] = (uint16_t)((e0 + (4 << 1)) | 1);
+                    }
                 }
             }
-            const int lc = (v0.x == v0.y && v0.x == v1.x && v0.x == v1.y) ? kLsChromaOne : kLsChromaCell;
+            const int lc = one ? kLsChromaOne : kLsChromaCell;
             sm.list[SM::list_off(lc) + atomicAdd(&sm.cnt[lc], 1)] = (uint16_t)qi;
             lm = (m.luma_mask >> lb0) & 0x33u;
             if (m.cbp_chroma) {
