@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--e2e-pics-per-step", type=int, default=4, help="pictures of every lane per step of the end-to-end leg (PCIe-bound, ~16 ms per picture of 256 lanes)")
     ap.add_argument("--check-lanes", type=int, default=8, help="lanes whose reference rings are byte-compared with the oracle after the timed loops (0 = no parity gate)")
     ap.add_argument("--no-extras", action="store_true", help="skip the 4K / single-lane sub-runs")
+    ap.add_argument("--e2e-wire", default="v2", choices=["v1", "v2"], help="host->device syntax format of the end-to-end leg: v2 = compact FrameSyntax "
+                    "(0.62 MB per dense 1080p picture, expanded on the device), v1 = 96-byte records + 16 int16 slots per coded block (2.09 MB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-parts", default="hcd", help="debug: which legs the e2e step runs (h = H2D, c = compute, d = D2H)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -377,6 +379,34 @@ class Workload:
         self.fs_arrays = [(P.FrameSyntax * L)(*fss[t]) for t in range(T)]
         self.slot_arrays = [(C.c_int32 * L)(*[fss[t][l].hdr.dst_slot for l in range(L)]) for t in range(T)]
         self.out_host = None
+        self.v2_arrays = None
+
+    def pack_v2(self):
+        """the e2e leg's inputs in the compact wire format: every staged picture packed once (what a parser that emits v2
+        directly would hand over), the lanes of one step back to back in pinned memory = one H2D copy per step"""
+        P, lib, L = self.P, self.lib, self.L
+        self.v2_arrays, self.v2_bytes, self._p4 = [], [], []
+        for t in range(self.T):
+            need = [lib.p264b200_pack_v2_bound(self.mb_w, self.mb_h, self.fss[t][l].hdr.n_coef) for l in range(L)]
+            tmp = np.zeros(max(need) + 16, np.uint8)
+            o = (-tmp.ctypes.data) % 16
+            packed = []
+            for l in range(L):
+                v2, _ = P.pack_v2(self.fss[t][l], tmp[o : o + need[l]])
+                packed.append((v2, tmp[o : o + v2.blob_bytes].copy()))
+            total = sum(len(b) for _, b in packed)
+            arena, ptr = pinned_array(lib, total + 16, np.uint8)
+            self._p4.append(ptr)
+            at = (-arena.ctypes.data) % 16
+            arr = (P.FrameSyntaxV2 * L)()
+            for l, (v2, b) in enumerate(packed):
+                arena[at : at + len(b)] = b
+                v2.blob = arena.ctypes.data + at
+                arr[l] = v2
+                at += len(b)
+            self.v2_arrays.append(arr)
+            self.v2_bytes.append(total + L * (440 + 40))
+        self.h2d_per_pic = float(np.mean(self.v2_bytes))
 
     # one picture of every lane, syntax already resident in HBM
     def recon(self):
@@ -391,8 +421,11 @@ class Workload:
             self.fsz = W * H * 3 // 2
             self.out_host, self._p3 = pinned_array(lib, L * self.fsz, np.uint8)
         rc = 0
-        if "h" in parts:
-            rc |= lib.p264b200_stage_frames(eng._e, t, L, self.fs_arrays[t])        # H2D of this picture's inputs (pinned)
+        if "h" in parts:                                                            # H2D of this picture's inputs (pinned)
+            if self.v2_arrays is not None:
+                rc |= lib.p264b200_stage_frames_v2(eng._e, t, L, self.v2_arrays[t])
+            else:
+                rc |= lib.p264b200_stage_frames(eng._e, t, L, self.fs_arrays[t])
         if "c" in parts:
             rc |= lib.p264b200_recon_step(eng._e, t, L)
         if "d" in parts:
@@ -411,7 +444,7 @@ class Workload:
 
     def close(self):
         self.eng.close()
-        for p in (self._p1, self._p2, getattr(self, "_p3", None)):
+        for p in [self._p1, self._p2, getattr(self, "_p3", None)] + list(getattr(self, "_p4", [])):
             if p:
                 self.lib.p264b200_host_free(p)
 
@@ -494,6 +527,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- end-to-end leg through the C-ABI with host buffers
     e2e_ms, e2e_lanes, e2e_rings, e2e_last = None, [], {}, {}
     if not args.no_e2e:
+        if args.e2e_wire == "v2":
+            wl.pack_v2()
         for _ in range(args.warmup * Ke):
             wl.e2e_picture(args.e2e_parts)
         barrier()
@@ -593,7 +628,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if e2e_ms is not None:
         line["e2e"] = {"value": aggregate_value(world, L * Ke, e2e_ms), "unit": unit, "h2d_bytes_per_step": int(wl.h2d_per_pic * Ke),
-                       "d2h_bytes_per_step": int(wl.d2h_per_pic * Ke), "ms_per_step": e2e_ms, "pictures_per_lane_per_step": Ke}
+                       "d2h_bytes_per_step": int(wl.d2h_per_pic * Ke), "ms_per_step": e2e_ms, "pictures_per_lane_per_step": Ke,
+                       "wire_format": f"FrameSyntax {args.e2e_wire}" + (" (compact: partition vectors + significance masks + int8 levels, expanded on the device)" if args.e2e_wire == "v2" else "")}
     wl.close()
     del wl
 

@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define P264B200_ABI_VERSION 1
+#define P264B200_ABI_VERSION 2   /* 2: FrameSyntax v2 (compact wire format) added; every v1 entry point is unchanged */
 
 /* error codes */
 #define P264B200_OK          0
@@ -115,6 +115,23 @@ typedef struct p264b200_frame_syntax {
     const int16_t     *coefs;         /* n_coef levels                                         */
 } p264b200_frame_syntax;
 
+/*
+ * FrameSyntax v2 -- the compact wire format (ABI version 2).  Same picture, fewer bytes over PCIe: the 32-byte tail of every
+ * macroblock record (all fields but mv[16]), one vector per PARTITION, and per coded block a 16-bit significance mask +
+ * its non-zero levels (int8 when every level of the picture fits).  A dense synthetic 1080p P picture shrinks from 2.09 MB
+ * to about 0.65 MB.  The engine expands it into the v1 staging layout on the device, so reconstruction is identical
+ * (csrc/host/wire_v2.cc documents the sections; p264b200_pack_v2 produces them from a v1 FrameSyntax).
+ */
+#define P264B200_V2_LEVELS8 1u        /* flags: the level stream is int8 */
+typedef struct p264b200_frame_syntax_v2 {
+    p264b200_frame_hdr hdr;           /* as v1 (n_coef = size of the EXPANDED coefficient stream)           */
+    const uint8_t *blob;              /* the packed picture, 16-byte aligned                                 */
+    uint32_t blob_bytes;
+    uint32_t flags;
+    uint32_t off_hdr, off_offs, off_mv, off_mask, off_level;   /* section offsets inside blob (16-byte aligned) */
+    uint32_t reserved[3];
+} p264b200_frame_syntax_v2;
+
 /* ------------------------------------------------------------------------- *
  * Engine: L independent lanes (streams / closed GOPs) reconstructed per launch
  * ------------------------------------------------------------------------- */
@@ -151,6 +168,16 @@ int  p264b200_stage_frame(p264b200_engine *e, int step, int lane, const p264b200
 
 /* Batched form: lanes [0, n) of one step from an array of n FrameSyntax (one call instead of n). */
 int  p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_frame_syntax *fs);
+
+/* v2 (compact) form of p264b200_stage_frames: copies the packed pictures (one copy for the whole step when the blobs lie
+ * back to back in host memory, each starting on the next 16-byte boundary) and expands them on the device into the
+ * same staging area p264b200_stage_frames fills.  Asynchronous; same rules for the host buffers. */
+int  p264b200_stage_frames_v2(p264b200_engine *e, int step, int n, const p264b200_frame_syntax_v2 *fs);
+/* host side of v2 (no GPU needed): pack a v1 FrameSyntax into dst (>= p264b200_pack_v2_bound bytes, 16-byte aligned),
+ * and the reference expander the device kernel is tested against */
+size_t p264b200_pack_v2_bound(int mb_w, int mb_h, uint32_t n_coef);
+int  p264b200_pack_v2(const p264b200_frame_syntax *fs, uint8_t *dst, size_t cap, p264b200_frame_syntax_v2 *out);
+int  p264b200_unpack_v2(const p264b200_frame_syntax_v2 *in, p264b200_mb *mbs, int16_t *coefs);
 
 /* Reconstruct staging step `step` for lanes [0, n_lanes): MC + IDCT + intra + deblock + border.
  * Asynchronous; inputs are already resident in HBM. */

@@ -69,6 +69,11 @@ class FrameSyntax(C.Structure):
     _fields_ = [("hdr", FrameHdr), ("mbs", C.c_void_p), ("coefs", C.c_void_p)]
 
 
+class FrameSyntaxV2(C.Structure):
+    _fields_ = [("hdr", FrameHdr), ("blob", C.c_void_p), ("blob_bytes", C.c_uint32), ("flags", C.c_uint32), ("off_hdr", C.c_uint32),
+                ("off_offs", C.c_uint32), ("off_mv", C.c_uint32), ("off_mask", C.c_uint32), ("off_level", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
 class EngineCfg(C.Structure):
     _fields_ = [
         ("device", C.c_int32),
@@ -133,6 +138,10 @@ def load_library() -> C.CDLL:
         "p264b200_stage_frame": (i32, [vp, i32, i32, C.POINTER(FrameSyntax)]),
         "p264b200_recon_step": (i32, [vp, i32, i32]),
         "p264b200_stage_frames": (i32, [vp, i32, i32, C.POINTER(FrameSyntax)]),
+        "p264b200_stage_frames_v2": (i32, [vp, i32, i32, C.POINTER(FrameSyntaxV2)]),
+        "p264b200_pack_v2_bound": (C.c_size_t, [i32, i32, C.c_uint32]),
+        "p264b200_pack_v2": (i32, [C.POINTER(FrameSyntax), u8p, C.c_size_t, C.POINTER(FrameSyntaxV2)]),
+        "p264b200_unpack_v2": (i32, [C.POINTER(FrameSyntaxV2), u8p, u8p]),
         "p264b200_frames_download": (i32, [vp, i32, C.POINTER(C.c_int32), u8p, C.c_size_t]),
         "p264b200_recon_frame": (i32, [vp, i32, C.POINTER(FrameSyntax)]),
         "p264b200_frame_upload": (i32, [vp, i32, i32, u8p, i32, u8p, u8p, i32]),
@@ -219,6 +228,30 @@ class Frame:
         fs.mbs = self.mbs.ctypes.data
         fs.coefs = self.coefs.ctypes.data
         return fs
+
+
+def pack_v2(fs: FrameSyntax, dst: np.ndarray | None = None):
+    """FrameSyntax v1 -> (FrameSyntaxV2, backing uint8 array): the compact wire format (no GPU needed).  `dst` (optional)
+    is a 16-byte aligned uint8 buffer of at least p264b200_pack_v2_bound bytes to pack into."""
+    lib = load_library()
+    need = lib.p264b200_pack_v2_bound(fs.hdr.mb_w, fs.hdr.mb_h, fs.hdr.n_coef)
+    if dst is None:
+        raw = np.empty(need + 16, np.uint8)
+        o = (-raw.ctypes.data) % 16
+        dst = raw[o : o + need]
+    out = FrameSyntaxV2()
+    _check(lib.p264b200_pack_v2(C.byref(fs), dst.ctypes.data, len(dst), C.byref(out)), "p264b200_pack_v2")
+    return out, dst
+
+
+def unpack_v2(v2: FrameSyntaxV2) -> "Frame":
+    """reference expander (host): FrameSyntaxV2 -> Frame"""
+    lib = load_library()
+    n = v2.hdr.mb_w * v2.hdr.mb_h
+    mbs = np.zeros(n, dtype=MB_DTYPE)
+    coefs = np.zeros(max(8, v2.hdr.n_coef), np.int16)
+    _check(lib.p264b200_unpack_v2(C.byref(v2), mbs.ctypes.data, coefs.ctypes.data), "p264b200_unpack_v2")
+    return Frame(FrameHdr.from_buffer_copy(v2.hdr), mbs, coefs[: max(8, v2.hdr.n_coef)])
 
 
 class Parser:
@@ -359,6 +392,11 @@ class Engine:
 
     def stage(self, step: int, lane: int, fs: FrameSyntax):
         _check(self._lib.p264b200_stage_frame(self._e, step, lane, C.byref(fs)), "p264b200_stage_frame")
+
+    def stage_v2(self, step: int, frames_v2):
+        """lanes [0, len) of one step from packed (v2) pictures"""
+        arr = (FrameSyntaxV2 * len(frames_v2))(*frames_v2)
+        _check(self._lib.p264b200_stage_frames_v2(self._e, step, len(frames_v2), arr), "p264b200_stage_frames_v2")
 
     def recon_step(self, step: int, n_lanes: int | None = None):
         _check(self._lib.p264b200_recon_step(self._e, step, n_lanes or self.lanes), "p264b200_recon_step")

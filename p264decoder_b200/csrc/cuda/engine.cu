@@ -17,6 +17,7 @@
 #include "border.cuh"
 #include "common.cuh"
 #include "deblock.cuh"
+#include "expand_v2.cuh"
 #include "recon_inter.cuh"
 #include "recon_intra.cuh"
 
@@ -61,6 +62,10 @@ struct p264b200_engine {
     int16_t *d_coefs = nullptr;
     FrameDesc *d_descs = nullptr, *h_descs = nullptr;
     size_t coef_cap = 0;  // int16 per lane per step
+    // FrameSyntax v2: packed pictures [step][lanes x blob capacity] + their section tables (lazy, first p264b200_stage_frames_v2)
+    uint8_t *d_blob = nullptr;
+    size_t blob_cap = 0;           // bytes per lane per step
+    V2Desc *d_v2 = nullptr, *h_v2 = nullptr;
     uint8_t *d_out = nullptr;      // [lanes] tight I420 pictures for the batched download (lazy)
     size_t out_bytes = 0;
     PackSrc *d_pack = nullptr;     // [lanes][n_slots] plane origins
@@ -206,6 +211,9 @@ void p264b200_engine_destroy(p264b200_engine *e)
     cudaFree(e->d_out);
     cudaFree(e->d_pack);
     cudaFree(e->d_intra);
+    cudaFree(e->d_blob);
+    cudaFree(e->d_v2);
+    if (e->h_v2) cudaFreeHost(e->h_v2);
     if (e->h_descs) cudaFreeHost(e->h_descs);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->s_h2d) cudaStreamSynchronize(e->s_h2d);
@@ -471,6 +479,67 @@ int p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_fr
     }
     CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
     memset(&e->desc_queued[s0], 1, n);
+    CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
+    e->h2d_busy = true;
+    return P264B200_OK;
+}
+
+int p264b200_stage_frames_v2(p264b200_engine *e, int step, int n, const p264b200_frame_syntax_v2 *fs)
+{
+    if (!e || !fs || n < 1 || n > e->cfg.lanes || step < 0 || step >= e->cfg.stage_steps) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t n_mb = (size_t)e->g.mb_w * e->g.mb_h;
+    const size_t slots = (size_t)e->cfg.stage_steps * e->cfg.lanes;
+    if (!e->d_blob) {
+        e->blob_cap = p264b200_pack_v2_bound(e->g.mb_w, e->g.mb_h, (uint32_t)e->coef_cap);
+        CK(cudaMalloc(&e->d_blob, slots * e->blob_cap));
+        CK(cudaMalloc(&e->d_v2, slots * sizeof(V2Desc)));
+        CK(cudaMallocHost(&e->h_v2, slots * sizeof(V2Desc)));
+    }
+    // v1-shaped FrameDesc (plane pointers, slice parameters) for every lane; the records / levels it points at are
+    // written by the expansion kernel below
+    for (int l = 0; l < n; l++) {
+        if (!fs[l].blob || fs[l].blob_bytes > e->blob_cap || ((uintptr_t)fs[l].blob & 15)) {
+            set_err("p264b200_stage_frames_v2: packed picture missing, misaligned or larger than the engine's bound", cudaSuccess);
+            return P264B200_EINVAL;
+        }
+        p264b200_frame_syntax v1;
+        v1.hdr = fs[l].hdr;
+        v1.mbs = reinterpret_cast<const p264b200_mb *>(fs[l].blob);   // (only tested for non-NULL)
+        v1.coefs = reinterpret_cast<const int16_t *>(fs[l].blob);
+        const int r = prepare_desc(e, step, l, &v1);
+        if (r) return r;
+    }
+    const size_t s0 = (size_t)step * e->cfg.lanes;
+    uint8_t *dbase = e->d_blob + s0 * e->blob_cap;
+    bool contiguous = true;
+    size_t total = 0;
+    for (int l = 0; l < n; l++) {
+        if (l && fs[l].blob != fs[0].blob + total) contiguous = false;
+        total += ((size_t)fs[l].blob_bytes + 15) & ~(size_t)15;
+    }
+    contiguous = contiguous && total <= (size_t)n * e->blob_cap;
+    size_t at = 0;
+    for (int l = 0; l < n; l++) {
+        V2Desc &d = e->h_v2[s0 + l];
+        d.blob = contiguous ? dbase + at : dbase + (size_t)l * e->blob_cap;
+        d.off_hdr = fs[l].off_hdr, d.off_offs = fs[l].off_offs, d.off_mv = fs[l].off_mv, d.off_mask = fs[l].off_mask, d.off_level = fs[l].off_level;
+        d.flags = fs[l].flags, d.n_coef = fs[l].hdr.n_coef, d.pad = 0;
+        at += ((size_t)fs[l].blob_bytes + 15) & ~(size_t)15;
+    }
+    CK(cudaStreamWaitEvent(e->s_h2d, e->ev_recon[step], 0));
+    if (contiguous) {
+        CK(cudaMemcpyAsync(dbase, fs[0].blob, total, cudaMemcpyHostToDevice, e->s_h2d));
+    } else {
+        for (int l = 0; l < n; l++)
+            CK(cudaMemcpyAsync(dbase + (size_t)l * e->blob_cap, fs[l].blob, fs[l].blob_bytes, cudaMemcpyHostToDevice, e->s_h2d));
+    }
+    CK(cudaMemcpyAsync(e->d_v2 + s0, &e->h_v2[s0], (size_t)n * sizeof(V2Desc), cudaMemcpyHostToDevice, e->s_h2d));
+    CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
+    memset(&e->desc_queued[s0], 1, n);
+    e->launches++;
+    expand_v2_kernel<<<dim3((unsigned)((n_mb + 127) / 128), n), 128, 0, e->s_h2d>>>(e->d_v2 + s0, e->d_descs + s0, (int)n_mb);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev_staged[step], e->s_h2d));
     e->h2d_busy = true;
     return P264B200_OK;

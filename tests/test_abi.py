@@ -40,7 +40,7 @@ def test_no_cuda_runtime_dependency_leaks():
 
 def test_struct_sizes():
     lib = P.load_library()
-    assert lib.p264b200_abi_version() == 1
+    assert lib.p264b200_abi_version() == 2
     assert P.MB_DTYPE.itemsize == 96
     assert C.sizeof(P.FrameHdr) == 124
     assert C.sizeof(P.FrameSyntax) == 144

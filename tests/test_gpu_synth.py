@@ -168,6 +168,36 @@ def test_randomised_stress_time_boxed():
     assert cases >= 1
 
 
+def test_wire_format_v2_staging_matches_oracle():
+    """FrameSyntax v2: packed pictures laid back to back in one host arena (one H2D copy), expanded on the device, alternating
+    with v1 staging of the other step slot; every picture byte-identical to the oracle."""
+    mb_w, mb_h, lanes, steps = 11, 9, 5, 6
+    eng = P.Engine(mb_w, mb_h, n_slots=3, lanes=lanes, stage_steps=2)
+    rings = [O.OracleFrames(mb_w, mb_h, 3) for _ in range(lanes)]
+    syns = [P.Synth(mb_w, mb_h, n_refs=2, seed=500 + l, intra_pct=10 if l != 2 else 100, sweep_offsets=1, max_level=8 if l else 900) for l in range(lanes)]
+    lib = P.load_library()
+    for s in range(steps):
+        frames = [sy.next() for sy in syns]
+        if s % 3 == 2:
+            for l, fr in enumerate(frames):
+                eng.stage(s % 2, l, fr.syntax())
+        else:
+            need = [lib.p264b200_pack_v2_bound(mb_w, mb_h, fr.hdr.n_coef) for fr in frames]
+            raw = np.zeros(sum(need) + 16, np.uint8)
+            o = (-raw.ctypes.data) % 16
+            v2s, at = [], o
+            for fr, nd in zip(frames, need):
+                v2, _ = P.pack_v2(fr.syntax(), raw[at : at + nd])
+                v2s.append(v2)
+                at += v2.blob_bytes if s % 2 == 0 else nd      # even steps: tightly back to back (one copy); odd: gaps (per-lane copies)
+            eng.stage_v2(s % 2, v2s)
+        eng.recon_step(s % 2, lanes)
+        eng.sync()
+        for l, fr in enumerate(frames):
+            _compare(eng.download(l, fr.hdr.dst_slot), rings[l].recon(fr), fr, f"v2 step {s} lane {l}")
+    eng.close()
+
+
 def test_batched_stage_and_packed_download_match_per_picture_path():
     """p264b200_stage_frames / p264b200_frames_download (pack kernel + one contiguous D2H) against the
     per-picture calls, pipelined over several steps without intermediate syncs."""

@@ -163,3 +163,30 @@ def test_gop_scan_f26():
     assert gops[0][0] == 0
     for off, _ in gops:
         assert bytes(data[off : off + 4]) == b"\x00\x00\x00\x01" and (data[off + 4] & 0x1f) in (6, 7)   # SEI / SPS first
+
+
+@pytest.mark.parametrize("kw", [dict(intra_pct=10, n_refs=2), dict(intra_pct=0, sub8x8=0, max_level=2000, qp_min=0, qp_max=51, coded_pct=60), dict(first_intra=1),
+                                dict(coded_pct=0, skip_pct=60), dict(first_intra=0)])
+def test_wire_format_v2_round_trip(kw):
+    """FrameSyntax v2 (compact wire format): pack -> reference unpack reproduces every field a kernel reads -- all vectors,
+    the record tails, every coefficient -- and is at least 2.5x smaller on the bench-shaped stream."""
+    mb_w, mb_h = 13, 7
+    syn = P.Synth(mb_w, mb_h, seed=17, **kw)
+    for _ in range(4):
+        fr = syn.next()
+        fs = fr.syntax()
+        v2, blob = P.pack_v2(fs)
+        assert v2.blob_bytes <= len(blob) and v2.blob_bytes % 16 == 0
+        back = P.unpack_v2(v2)
+        a, b = fr.mbs.copy(), back.mbs.copy()
+        inter = a["mb_type"] > P.MB_I16x16
+        for arr in (a, b):
+            arr["reserved"] = 0
+            arr["i4_mode"][inter] = 0
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        assert np.array_equal(fr.coefs[: fr.hdr.n_coef], back.coefs[: fr.hdr.n_coef])
+        v1_bytes = fr.mbs.nbytes + 2 * fr.hdr.n_coef
+        if kw.get("max_level", 8) <= 127:
+            assert v2.flags & 1
+        if kw == dict(first_intra=0):   # the bench-shaped stream: all partition shapes, 25 % coded blocks
+            assert v2.blob_bytes * 2.5 < v1_bytes
