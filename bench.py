@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="1080p", choices=list(SIZES))
     ap.add_argument("--lanes", type=int, default=256, help="independent streams per GPU per launch (the deblock wavefront ramp amortises with lanes: 64 -> 69 k, 256 -> 87 k pictures/s)")
-    ap.add_argument("--staged", type=int, default=2, help="distinct pre-staged pictures per lane (cycled)")
+    ap.add_argument("--staged", type=int, default=4, help="distinct pre-staged pictures per lane (cycled); picture i of a stream has slice QP 20 + 2 * (i mod 11), "
+                    "so 4 staged pictures cover QP 20..26 (both dequant branches), 11 the whole 20..40 sweep")
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--intra-pct", type=int, default=0, help="side workload: %% of intra macroblocks inside the P pictures (0 = the headline workload)")
     ap.add_argument("--pics-per-step", type=int, default=24, help="consecutive pictures of every lane per timed step (device-resident leg): "
@@ -258,7 +259,8 @@ def workload_config(args, lanes):
     mb_w, mb_h = SIZES[args.size]
     return {
         "workload": f"BASELINE.json configs[2]: synthetic {args.size} P-frame streams ({16*mb_w}x{16*mb_h} coded), "
-                    f"random qpel MVs over all partition shapes incl. sub-8x8, 25% coded 4x4 blocks, slice QP sweep 20..40, "
+                    f"random qpel MVs over all partition shapes incl. sub-8x8, 25% coded 4x4 blocks, slice QP sweep 20..40 in steps of 2 per picture "
+                    f"(the {args.staged} staged pictures per lane cover QP 20..{20 + 2 * (min(args.staged, 11) - 1)}), "
                     f"deblocking on, {args.refs} reference frame(s)" + (f", {args.intra_pct}% intra macroblocks" if args.intra_pct else ""),
         "lanes_per_gpu": lanes, "staged_pictures_per_lane": args.staged, "mb_per_picture": mb_w * mb_h,
         "l2_policy": "inputs larger than L2: every step streams lanes x (syntax + reference + output picture) >> 126 MB",

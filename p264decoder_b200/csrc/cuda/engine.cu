@@ -48,6 +48,9 @@ struct p264b200_engine {
     // Host-buffer path: syntax uploads, kernels and picture downloads run on three streams so that
     // H2D of step n+1, reconstruction of step n and D2H of step n-1 overlap (PCIe is full duplex).
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // the boundary-strength pre-pass reads syntax only, so it runs beside recon_inter on its own stream and joins before deblock
+    cudaStream_t s_side = nullptr;
+    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     std::vector<cudaEvent_t> ev_staged;            // [step] last upload into that staging slot
     std::vector<cudaEvent_t> ev_recon;             // [step] reconstruction that consumed that slot
     std::vector<cudaEvent_t> ev_d2h_slot;          // [frame slot] last download of that ring slot (any lane)
@@ -98,6 +101,8 @@ struct p264b200_engine {
     int inter_variant = 2;  // P264B200_INTER_VARIANT: CTA shape / register budget / tile height of recon_inter: 0 = 512 threads x 2 CTAs per SM
                             // (64 registers), 1 = 512 x 3 (40), 2 = 384 x 3 (56, default), 3 = 256 x 4 (64); 8x16-macroblock tiles: 4 = 576 x 2 (56),
                             // 5 = 512 x 2 (64), 6 = 768 x 1 (80)
+    bool no_side = true;   // P264B200_NO_SIDE=0: run the boundary-strength pre-pass on a side stream beside recon_inter (measured: step 2.780 ->
+                           // 2.764 ms, but the pre-pass then shares the SMs for the whole 1.5 ms and the per-kernel profile stops adding up; off by default)
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
     int trace_ticket = -1;  // P264B200_TRACE: deblock CTA (by ticket) whose per-step cycle marks are recorded
 
@@ -222,6 +227,9 @@ void p264b200_engine_destroy(p264b200_engine *e)
         for (auto ev : *vec)
             if (ev) cudaEventDestroy(ev);
     if (e->ev_compute) cudaEventDestroy(e->ev_compute);
+    if (e->s_side) cudaStreamSynchronize(e->s_side), cudaStreamDestroy(e->s_side);
+    if (e->ev_side_fork) cudaEventDestroy(e->ev_side_fork);
+    if (e->ev_side_join) cudaEventDestroy(e->ev_side_join);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -255,6 +263,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     e->cfg = *cfg;
     if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
     if (const char *d = getenv("P264B200_TRACE")) e->trace_ticket = atoi(d);
+    if (const char *d = getenv("P264B200_NO_SIDE")) e->no_side = atoi(d) != 0;
     // measured (256 lanes x 1080p): 1 group 3.05 ms per step; 2 groups pipelined across steps (one group's deblock beside the
     // other's recon_inter, priority streams) 3.15 ms; with deblock held to one CTA per SM (P264B200_DBF_PAD=100) 3.46 ms; 4 groups
     // 3.63 ms -- both kernels lean on the same L1 / shared-memory data pipe (82 % and 67 % alone), so sharing the SMs buys nothing
@@ -301,6 +310,9 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (!rc && (err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
     if (!rc && (err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
     if (!rc && (err = cudaEventCreateWithFlags(&e->ev_compute, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    if (!rc && (err = cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking)) != cudaSuccess) fail("stream", err);
+    if (!rc && (err = cudaEventCreateWithFlags(&e->ev_side_fork, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
+    if (!rc && (err = cudaEventCreateWithFlags(&e->ev_side_join, cudaEventDisableTiming)) != cudaSuccess) fail("event", err);
     e->ev_staged.assign(cfg->stage_steps, nullptr);
     e->ev_recon.assign(cfg->stage_steps, nullptr);
     e->ev_d2h_slot.assign(cfg->n_slots, nullptr);
@@ -589,6 +601,19 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         const bool intra = flags & 1, dbf = flags & 2, pslice = flags & 4;
         const FrameDesc *descs = descs0 + l0;
         int *tickets = e->d_sync + p264b200_engine::kSyncHdr * gi;
+        // boundary strengths depend on the syntax alone: with one lane group the pre-pass runs on the side stream, beside
+        // recon_inter (it starts once everything queued before this step is done -- the previous picture's deblock reads
+        // the same strength buffer), and the main stream waits for it in front of deblock
+        const bool bs_aside = dbf && pslice && G == 1 && !e->no_side;
+        if (bs_aside) {
+            CK(cudaEventRecord(e->ev_side_fork, st));
+            CK(cudaStreamWaitEvent(e->s_side, e->ev_side_fork, 0));
+            {
+                ProfScope p(e, K_DEBLOCK_BS, e->s_side);
+                deblock_bs_kernel<<<dim3((n_mb + 127) / 128, nl), 128, 0, e->s_side>>>(descs, g);
+            }
+            CK(cudaEventRecord(e->ev_side_join, e->s_side));
+        }
         if (pslice) {
             ProfScope p(e, K_INTER, st);
             const int th = e->inter_variant >= 7 ? 4 : e->inter_variant >= 4 ? 16 : 8;
@@ -613,7 +638,9 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
             CK(cudaMemsetAsync(e->d_sync + p264b200_engine::kSyncHdr * p264b200_engine::kMaxGroups + (size_t)l0 * 3 * g.mb_h, 0, (size_t)nl * 3 * g.mb_h * sizeof(int), sh));
         }
         st = sh;
-        if (dbf) {
+        if (bs_aside) {
+            CK(cudaStreamWaitEvent(st, e->ev_side_join, 0));
+        } else if (dbf) {
             ProfScope p(e, K_DEBLOCK_BS, st);
             deblock_bs_kernel<<<dim3((n_mb + 127) / 128, nl), 128, 0, st>>>(descs, g);
         }
