@@ -333,7 +333,8 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
             {(const void *)recon_inter_kernel<384, 3, 8>, (int)sizeof(InterSmem<8>)},   {(const void *)recon_inter_kernel<256, 4, 8>, (int)sizeof(InterSmem<8>)},
             {(const void *)recon_inter_kernel<576, 2, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<512, 2, 16>, (int)sizeof(InterSmem<16>)},
             {(const void *)recon_inter_kernel<768, 1, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<192, 6, 4>, (int)sizeof(InterSmem<4>)},
-            {(const void *)recon_inter_kernel<256, 4, 4>, (int)sizeof(InterSmem<4>)}};
+            {(const void *)recon_inter_kernel<256, 4, 4>, (int)sizeof(InterSmem<4>)},   {(const void *)recon_inter_kernel<384, 4, 8>, (int)sizeof(InterSmem<8>)},
+            {(const void *)recon_inter_kernel<320, 4, 8>, (int)sizeof(InterSmem<8>)}};
         for (auto &k : kern)
             if (!rc && (err = cudaFuncSetAttribute(k.first, cudaFuncAttributeMaxDynamicSharedMemorySize, k.second)) != cudaSuccess)
                 fail("cudaFuncSetAttribute(recon_inter)", err);
@@ -627,6 +628,8 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
             case 6: recon_inter_kernel<768, 1, 16><<<grid, 768, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
             case 7: recon_inter_kernel<192, 6, 4><<<grid, 192, sizeof(InterSmem<4>), st>>>(descs, g, e->dbg); break;
             case 8: recon_inter_kernel<256, 4, 4><<<grid, 256, sizeof(InterSmem<4>), st>>>(descs, g, e->dbg); break;
+            case 9: recon_inter_kernel<384, 4, 8><<<grid, 384, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 10: recon_inter_kernel<320, 4, 8><<<grid, 320, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
             default: recon_inter_kernel<384, 3, 8><<<grid, 384, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
             }
         }

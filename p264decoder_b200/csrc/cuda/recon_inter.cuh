@@ -485,18 +485,16 @@ template <int TH>
 struct InterSmem {
     static constexpr int kMbs = kTileW * TH;
     static constexpr int kLumaCap = 16 * kMbs, kQuadCap = 4 * kMbs;
-    static constexpr int kListEntries = 6 * kLumaCap + 2 * kQuadCap;
     static constexpr int kResCap = 24 * kMbs;
-    __host__ __device__ static constexpr int list_off(int li)
-    {
-        return li < kLsChromaCell ? li * kLumaCap : li == kLsChromaCell ? 5 * kLumaCap : li == kLsChromaOne ? 5 * kLumaCap + kQuadCap : 5 * kLumaCap + 2 * kQuadCap;
-    }
     p264b200_mb mb[kMbs];                           // the tile's macroblock records
     // picture tile.  Rows are padded by 8 bytes: with a pitch of exactly 32 (16) banks every row of a 4x4 block falls
     // into the same bank, so the 16 blocks of one macroblock were a 4-way conflict on every tile access
     uint8_t y[16 * TH][kYPitch];                    // luma
     uint8_t c[2][8 * TH][kCPitch];                  // Cb / Cr
-    uint16_t list[kListEntries];                    // work lists: luma item = mb << 5 | b << 1 | half, quadrant = mb << 2 | q
+    // Work lists, compact: the six luma lists lie back to back in `luma` (counted first, placed after a barrier), because
+    // every kilobyte of shared memory is a kilobyte less L1 for the reference windows (worst-case-sized lists: 13 KB per CTA)
+    uint16_t luma[kLumaCap];                        // luma item = mb << 5 | b << 1 | half
+    uint16_t chroma[2][kQuadCap];                   // [per-cell vectors, one vector]: quadrant = mb << 2 | q
     uint16_t res[kResCap];                          // residual work: full blocks (luma: mb << 4 | b, chroma: 16 * kMbs + (mb << 3 | cb)) from the
                                                     //   front, DC-only chroma blocks from the back
     const uint8_t *ref[kMaxRefs][3];
@@ -504,6 +502,8 @@ struct InterSmem {
     int nres[2];                                    // full / DC-only residual blocks
     int ticket;                                     // next chunk of the prediction pass
 };
+// storage order of the luma lists inside InterSmem::luma = processing order with the copy list last
+__device__ __forceinline__ int luma_slot(int li) { return li == kLsCopy ? 5 : li; }
 __device__ __forceinline__ int luma_list(int cls) { return cls == kMcCopy ? kLsCopy : kMcCentreH - cls; }
 __device__ __forceinline__ int list_class(int li) { return li == kLsCopy ? kMcCopy : kMcCentreH - li; }
 
@@ -607,9 +607,10 @@ __global__ void __launch_bounds__(THREADS, MINB) recon_inter_kernel(const FrameD
     // ---- classify, one thread per 8x8 quadrant: strips / blocks by interpolation class, chroma by "one vector for the
     // quadrant", and the blocks that carry residual (one position range per quadrant from a warp scan + one atomic per warp).
     const int lane = tid & 31;
-#pragma unroll 1
-    for (int qi = tid; qi < 4 * kMbs; qi += THREADS) {
-        const int mb = qi >> 2, q = qi & 3;
+    static_assert(4 * kMbs <= THREADS, "one quadrant per thread: its luma items wait in registers for the placement pass");
+    uint32_t slot[4] = {0, 0, 0, 0};
+    if (tid < 4 * kMbs) {
+        const int qi = tid, mb = qi >> 2, q = qi & 3;
         const p264b200_mb &m = sm.mb[mb];
         const bool inter = !P264B200_IS_INTRA(m.mb_type);
         const int lb0 = 8 * (q >> 1) + 2 * (q & 1);
@@ -624,30 +625,31 @@ __global__ void __launch_bounds__(THREADS, MINB) recon_inter_kernel(const FrameD
             }
             const int2 v0 = *reinterpret_cast<const int2 *>(m.mv[lb0]), v1 = *reinterpret_cast<const int2 *>(m.mv[lb0 + 4]);
             const bool one = v0.x == v0.y && v0.x == v1.x && v0.x == v1.y;
+            // luma items are COUNTED here and placed after the barrier (slot = 1 << 31 | list << 27 | position << 16 | item)
             if (one) {
                 // one vector for the quadrant (every partition of 8x8 and up): its two strips sit side by side in the list, so
                 // that the lanes of a 16-wide partition read the same cache lines in the same load instruction
                 const int l0 = luma_list(mc_class(v0.x & 3, (v0.x >> 16) & 3));
-                const int pos = SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 2);
-                sm.list[pos] = (uint16_t)(mb << 5 | lb0 << 1);
-                sm.list[pos + 1] = (uint16_t)(mb << 5 | (lb0 + 1) << 1);
+                const uint32_t pos = (uint32_t)atomicAdd(&sm.cnt[l0], 2);
+                slot[0] = 0x80000000u | (uint32_t)l0 << 27 | pos << 16 | (uint32_t)(mb << 5 | lb0 << 1);
+                slot[1] = slot[0] + (1u << 16) + 2u;
             } else {
 #pragma unroll
                 for (int sx = 0; sx < 2; sx++) {
                     const int top = sx ? v0.y : v0.x, bot = sx ? v1.y : v1.x;
                     const int l0 = luma_list(mc_class(top & 3, (top >> 16) & 3));
-                    const int e0 = mb << 5 | (lb0 + sx) << 1;
+                    const uint32_t e0 = (uint32_t)(mb << 5 | (lb0 + sx) << 1);
                     if (top == bot) {
-                        sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)e0;
+                        slot[2 * sx] = 0x80000000u | (uint32_t)l0 << 27 | (uint32_t)atomicAdd(&sm.cnt[l0], 1) << 16 | e0;
                     } else {
                         const int l1 = luma_list(mc_class(bot & 3, (bot >> 16) & 3));
-                        sm.list[SM::list_off(l0) + atomicAdd(&sm.cnt[l0], 1)] = (uint16_t)(e0 | 1);
-                        sm.list[SM::list_off(l1) + atomicAdd(&sm.cnt[l1], 1)] = (uint16_t)((e0 + (4 << 1)) | 1);
+                        slot[2 * sx] = 0x80000000u | (uint32_t)l0 << 27 | (uint32_t)atomicAdd(&sm.cnt[l0], 1) << 16 | e0 | 1u;
+                        slot[2 * sx + 1] = 0x80000000u | (uint32_t)l1 << 27 | (uint32_t)atomicAdd(&sm.cnt[l1], 1) << 16 | (e0 + (4u << 1)) | 1u;
                     }
                 }
             }
             const int lc = one ? kLsChromaOne : kLsChromaCell;
-            sm.list[SM::list_off(lc) + atomicAdd(&sm.cnt[lc], 1)] = (uint16_t)qi;
+            sm.chroma[lc - kLsChromaCell][atomicAdd(&sm.cnt[lc], 1)] = (uint16_t)qi;
             lm = (m.luma_mask >> lb0) & 0x33u;
             if (m.cbp_chroma) {
                 cfull = ((m.chroma_mask >> q) & 1u) | (((m.chroma_mask >> (4 + q)) & 1u) << 1);
@@ -680,10 +682,35 @@ __global__ void __launch_bounds__(THREADS, MINB) recon_inter_kernel(const FrameD
     }
     __syncthreads();
 
+    // ---- placement: the luma lists back to back in storage order (luma_slot)
+    if (tid < 4 * kMbs) {
+        int off[6];
+        off[0] = 0;
+#pragma unroll
+        for (int k = 1; k < 6; k++) off[k] = off[k - 1] + sm.cnt[k - 1 == 5 ? kLsCopy : k - 1];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (slot[k] >> 31) {
+                const int sl = luma_slot((slot[k] >> 27) & 7);
+                int o = 0;
+#pragma unroll
+                for (int j = 1; j < 6; j++) o = sl == j ? off[j] : o;
+                sm.luma[o + ((slot[k] >> 16) & 0x7ff)] = (uint16_t)(slot[k] & 0xffff);
+            }
+    }
+    __syncthreads();
+
     // ---- prediction: the warps draw class-pure chunks of 32 items by ticket, heaviest lists first.  Lanes 0..7 hold the
     // chunk range [start, end) of list `lane`; a ticket's list is the number of lists that end at or before it.
     if (!(dbg & 1)) {
         const int n_l = lane < kLsCount ? sm.cnt[lane] : 0;
+        // where list `lane` starts inside its storage array
+        int soff = 0;
+        if (lane < kLsCount && lane != kLsChromaCell && lane != kLsChromaOne) {
+            const int sl = luma_slot(lane);
+#pragma unroll
+            for (int k = 0; k < 5; k++) soff += k < sl ? sm.cnt[k] : 0;
+        }
         int end = (n_l + 31) >> 5;
         const int nch = end;
 #pragma unroll
@@ -699,12 +726,12 @@ __global__ void __launch_bounds__(THREADS, MINB) recon_inter_kernel(const FrameD
             int t = 0;
             if (lane == 0) t = atomicAdd(&sm.ticket, 1);   // drawn ahead: the atomic's latency hides behind the chunk
             const int idx = 32 * (ticket - __shfl_sync(0xffffffffu, start, li)) + lane;
+            const int so = __shfl_sync(0xffffffffu, soff, li);
             if (idx < __shfl_sync(0xffffffffu, n_l, li)) {
-                const int e = sm.list[SM::list_off(li) + idx];
                 if (li == kLsChromaCell || li == kLsChromaOne)
-                    predict_chroma(sm, g, mbx0, mby0, e, li == kLsChromaOne);
+                    predict_chroma(sm, g, mbx0, mby0, sm.chroma[li - kLsChromaCell][idx], li == kLsChromaOne);
                 else
-                    predict_luma(sm, g, mbx0, mby0, e, list_class(li));
+                    predict_luma(sm, g, mbx0, mby0, sm.luma[so + idx], list_class(li));
             }
             ticket = __shfl_sync(0xffffffffu, t, 0);
         }

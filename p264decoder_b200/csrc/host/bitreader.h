@@ -15,22 +15,16 @@ public:
     bool eof() const { return pos_ >= size_bits_; }
     size_t pos() const { return pos_; }
 
-    // peek up to 25 bits without consuming
+    // peek up to 25 bits without consuming.  A 64-bit window of the stream is cached (one unaligned big-endian load per
+    // ~5 reads instead of one per read: the block reader peeks and skips a few bits at a time)
     uint32_t show(int n) const {
         if (n <= 0) return 0;
-        size_t byte = pos_ >> 3;
-        int sh = pos_ & 7;
-        size_t nbytes = size_bits_ >> 3;
-        if (byte + 8 <= nbytes) {
-            // fast path: one unaligned big-endian 64-bit load (the host parser is the bottleneck of real-bitstream decode)
-            uint64_t w;
-            __builtin_memcpy(&w, p_ + byte, 8);
-            w = __builtin_bswap64(w);
-            return (uint32_t)((w << sh) >> (64 - n));
+        size_t off = pos_ - wpos_;          // wraps to a huge value when the window lies ahead of pos_
+        if (off + (size_t)n > 64) {
+            refill();
+            off = pos_ - wpos_;
         }
-        uint64_t w = 0;
-        for (int i = 0; i < 5; i++) w = (w << 8) | (byte + i < nbytes ? p_[byte + i] : 0);
-        return (uint32_t)((w >> (40 - sh - n)) & ((1ull << n) - 1));
+        return (uint32_t)((w_ << off) >> (64 - n));
     }
     void skip(int n) { pos_ += n; }
     uint32_t read(int n) {
@@ -75,9 +69,25 @@ public:
     }
 
 private:
+    void refill() const {
+        const size_t byte = pos_ >> 3, nbytes = size_bits_ >> 3;
+        wpos_ = byte << 3;
+        if (byte + 8 <= nbytes) {
+            uint64_t w;
+            __builtin_memcpy(&w, p_ + byte, 8);
+            w_ = __builtin_bswap64(w);
+        } else {
+            // tail of the payload: bytes past the end read as zero (core/bs.h behaviour)
+            uint64_t w = 0;
+            for (int i = 0; i < 8; i++) w = (w << 8) | (byte + i < nbytes ? p_[byte + i] : 0);
+            w_ = w;
+        }
+    }
     const uint8_t *p_;
     size_t size_bits_;
     size_t pos_;
+    mutable uint64_t w_ = 0;
+    mutable size_t wpos_ = ~(size_t)0 - 1024;   // bit position of the cached window's first bit (byte aligned); none yet
 };
 
 }  // namespace p264b200
