@@ -98,9 +98,9 @@ struct p264b200_engine {
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_mc[kMaxGroups] = {}, ev_hi_done[kMaxGroups] = {};
     int dbf_pad_bytes = 0;   // P264B200_DBF_PAD (KB): dynamic shared memory added to deblock CTAs = fewer of them per SM, room for recon_inter CTAs
     bool groups_dirty = false;  // group streams hold work the main stream has not joined yet
-    int inter_variant = 2;  // P264B200_INTER_VARIANT: CTA shape / register budget / tile height of recon_inter: 0 = 512 threads x 2 CTAs per SM
-                            // (64 registers), 1 = 512 x 3 (40), 2 = 384 x 3 (56, default), 3 = 256 x 4 (64); 8x16-macroblock tiles: 4 = 576 x 2 (56),
-                            // 5 = 512 x 2 (64), 6 = 768 x 1 (80)
+    int inter_variant = 0;  // P264B200_INTER_VARIANT: CTA shape of recon_inter.  0 (default) = 8x8-macroblock tiles, 384 threads x 3 CTAs per SM
+                            // (56 registers): 1.47 ms at 256 lanes; 1 = 512 threads x 2 (64 registers): 1.75 ms; 2 = 8x16 tiles, 576 x 2: 1.74 ms;
+                            // 3 = 8x4 tiles, 192 x 6: 1.53 ms.  (4 CTAs per SM at 40 / 48 registers: 2.2 ms.)
     bool no_side = true;   // P264B200_NO_SIDE=0: run the boundary-strength pre-pass on a side stream beside recon_inter (measured: step 2.780 ->
                            // 2.764 ms, but the pre-pass then shares the SMs for the whole 1.5 ms and the per-kernel profile stops adding up; off by default)
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
@@ -329,12 +329,8 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (const char *v = getenv("P264B200_INTER_VARIANT")) e->inter_variant = atoi(v);
     {
         const std::pair<const void *, int> kern[] = {
-            {(const void *)recon_inter_kernel<512, 2, 8>, (int)sizeof(InterSmem<8>)},   {(const void *)recon_inter_kernel<512, 3, 8>, (int)sizeof(InterSmem<8>)},
-            {(const void *)recon_inter_kernel<384, 3, 8>, (int)sizeof(InterSmem<8>)},   {(const void *)recon_inter_kernel<256, 4, 8>, (int)sizeof(InterSmem<8>)},
-            {(const void *)recon_inter_kernel<576, 2, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<512, 2, 16>, (int)sizeof(InterSmem<16>)},
-            {(const void *)recon_inter_kernel<768, 1, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<192, 6, 4>, (int)sizeof(InterSmem<4>)},
-            {(const void *)recon_inter_kernel<256, 4, 4>, (int)sizeof(InterSmem<4>)},   {(const void *)recon_inter_kernel<384, 4, 8>, (int)sizeof(InterSmem<8>)},
-            {(const void *)recon_inter_kernel<320, 4, 8>, (int)sizeof(InterSmem<8>)}};
+            {(const void *)recon_inter_kernel<384, 3, 8>, (int)sizeof(InterSmem<8>)}, {(const void *)recon_inter_kernel<512, 2, 8>, (int)sizeof(InterSmem<8>)},
+            {(const void *)recon_inter_kernel<576, 2, 16>, (int)sizeof(InterSmem<16>)}, {(const void *)recon_inter_kernel<192, 6, 4>, (int)sizeof(InterSmem<4>)}};
         for (auto &k : kern)
             if (!rc && (err = cudaFuncSetAttribute(k.first, cudaFuncAttributeMaxDynamicSharedMemorySize, k.second)) != cudaSuccess)
                 fail("cudaFuncSetAttribute(recon_inter)", err);
@@ -617,19 +613,13 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (pslice) {
             ProfScope p(e, K_INTER, st);
-            const int th = e->inter_variant >= 7 ? 4 : e->inter_variant >= 4 ? 16 : 8;
+            // CTA shape / tile height: the default and the three alternatives the measurements in DESIGN.md 7b refer to
+            const int th = e->inter_variant == 2 ? 16 : e->inter_variant == 3 ? 4 : 8;
             const dim3 grid((g.mb_w + kTileW - 1) / kTileW, (g.mb_h + th - 1) / th, nl);
             switch (e->inter_variant) {
-            case 0: recon_inter_kernel<512, 2, 8><<<grid, 512, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
-            case 1: recon_inter_kernel<512, 3, 8><<<grid, 512, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
-            case 3: recon_inter_kernel<256, 4, 8><<<grid, 256, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
-            case 4: recon_inter_kernel<576, 2, 16><<<grid, 576, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
-            case 5: recon_inter_kernel<512, 2, 16><<<grid, 512, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
-            case 6: recon_inter_kernel<768, 1, 16><<<grid, 768, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
-            case 7: recon_inter_kernel<192, 6, 4><<<grid, 192, sizeof(InterSmem<4>), st>>>(descs, g, e->dbg); break;
-            case 8: recon_inter_kernel<256, 4, 4><<<grid, 256, sizeof(InterSmem<4>), st>>>(descs, g, e->dbg); break;
-            case 9: recon_inter_kernel<384, 4, 8><<<grid, 384, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
-            case 10: recon_inter_kernel<320, 4, 8><<<grid, 320, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 1: recon_inter_kernel<512, 2, 8><<<grid, 512, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
+            case 2: recon_inter_kernel<576, 2, 16><<<grid, 576, sizeof(InterSmem<16>), st>>>(descs, g, e->dbg); break;
+            case 3: recon_inter_kernel<192, 6, 4><<<grid, 192, sizeof(InterSmem<4>), st>>>(descs, g, e->dbg); break;
             default: recon_inter_kernel<384, 3, 8><<<grid, 384, sizeof(InterSmem<8>), st>>>(descs, g, e->dbg); break;
             }
         }
