@@ -197,6 +197,16 @@ int  p264b200_frame_download(p264b200_engine *e, int lane, int slot,
  * I420 image (Y, then U, then V); picture_bytes >= width*height*3/2. */
 int  p264b200_frames_download(p264b200_engine *e, int n, const int32_t *slots, uint8_t *dst, size_t picture_bytes);
 
+/* Output without a device -> host copy of the samples:
+ *  - p264b200_frame_device_planes: the DEVICE addresses of a reconstructed picture's planes (sample 0,0 of Y, U, V; the
+ *    padded frame store, strides from p264b200_engine_geometry) for consumers that stay on the GPU (display, transcode,
+ *    analysis).  Valid until the ring slot is reconstructed into again; order your work after p264b200_engine_stream.
+ *  - p264b200_frames_md5: MD5 (RFC 1321) of the tight I420 image (Y, U, V back to back) of lane l's slots[l], computed on the
+ *    device, 16 bytes per lane into `digests` (host memory) -- the reference's own check ("decode, md5 the YUV") at 16 bytes
+ *    of PCIe traffic per picture.  Asynchronous like the downloads; a verification path (one thread per picture). */
+int  p264b200_frame_device_planes(p264b200_engine *e, int lane, int slot, void *planes[3]);
+int  p264b200_frames_md5(p264b200_engine *e, int n, const int32_t *slots, uint8_t *digests);
+
 int  p264b200_engine_sync(p264b200_engine *e);
 
 /* CUDA stream the engine launches on (cudaStream_t as void*), for external event timing */

@@ -143,6 +143,8 @@ def load_library() -> C.CDLL:
         "p264b200_pack_v2": (i32, [C.POINTER(FrameSyntax), u8p, C.c_size_t, C.POINTER(FrameSyntaxV2)]),
         "p264b200_unpack_v2": (i32, [C.POINTER(FrameSyntaxV2), u8p, u8p]),
         "p264b200_frames_download": (i32, [vp, i32, C.POINTER(C.c_int32), u8p, C.c_size_t]),
+        "p264b200_frames_md5": (i32, [vp, i32, C.POINTER(C.c_int32), u8p]),
+        "p264b200_frame_device_planes": (i32, [vp, i32, i32, C.POINTER(C.c_void_p * 3)]),
         "p264b200_recon_frame": (i32, [vp, i32, C.POINTER(FrameSyntax)]),
         "p264b200_frame_upload": (i32, [vp, i32, i32, u8p, i32, u8p, u8p, i32]),
         "p264b200_frame_download": (i32, [vp, i32, i32, u8p, i32, u8p, u8p, i32]),
@@ -419,6 +421,21 @@ class Engine:
         _check(self._lib.p264b200_frame_download(self._e, lane, slot, y.ctypes.data, self.width, u.ctypes.data, v.ctypes.data, self.width // 2), "p264b200_frame_download")
         self.sync()
         return y, u, v
+
+    def md5(self, slots):
+        """hex MD5 of the tight I420 picture in ring slot slots[l] of every lane l < len(slots), computed on the device"""
+        n = len(slots)
+        out = np.zeros(16 * n, np.uint8)
+        arr = (C.c_int32 * n)(*slots)
+        _check(self._lib.p264b200_frames_md5(self._e, n, arr, out.ctypes.data), "p264b200_frames_md5")
+        self.sync()
+        return [out[16 * l : 16 * l + 16].tobytes().hex() for l in range(n)]
+
+    def device_planes(self, lane: int, slot: int):
+        """device addresses of sample (0, 0) of the Y, U, V planes of a ring slot (zero-copy output)"""
+        pl = (C.c_void_p * 3)()
+        _check(self._lib.p264b200_frame_device_planes(self._e, lane, slot, C.byref(pl)), "p264b200_frame_device_planes")
+        return [int(p) for p in pl]
 
     def timer_start(self):
         _check(self._lib.p264b200_timer_start(self._e), "p264b200_timer_start")

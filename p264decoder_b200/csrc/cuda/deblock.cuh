@@ -252,7 +252,7 @@ constexpr int kDbfWarps = kDbfRows + 2;  // + the "in" and "out" warps that own 
 // Optional per-macroblock cycle trace of ONE CTA (engine debug knob P264B200_TRACE=<ticket>): [warp][x][marks]:
 // 0 top of the iteration, 1 before waiting for the rows above, 2 after that wait, 3 end of the iteration
 constexpr int kDbfTraceSteps = 320;
-__device__ long long g_dbf_trace[kDbfRows + 1][kDbfTraceSteps][6];
+__device__ long long g_dbf_trace[12][kDbfTraceSteps][6];
 __device__ long long g_dbf_cta_ns[2048][4];  // per ticket: %globaltimer at kernel entry, first macroblock, last macroblock, exit (row warp 0)
 __device__ __forceinline__ long long dbf_now_ns()
 {
@@ -326,13 +326,14 @@ __device__ __forceinline__ void sts_release(int *p, int v)
     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
+template <int ROWS>
 struct DbfSmem {
-    uint8_t tile[kDbfRows][kDbfQuad][kDbfTile];                  // luma: row r at 16r; chroma: plane p row r at 64p + 8r
-    uint8_t ring[kDbfRows + 1][kDbfRing][kDbfQuad][kDbfSlot];    // ring[0]: rows above warp 0 (filled by the in warp from global memory);
+    uint8_t tile[ROWS][kDbfQuad][kDbfTile];                  // luma: row r at 16r; chroma: plane p row r at 64p + 8r
+    uint8_t ring[ROWS + 1][kDbfRing][kDbfQuad][kDbfSlot];    // ring[0]: rows above warp 0 (filled by the in warp from global memory);
                                                                  // ring[1 + w]: last rows of warp w's macroblocks.  luma: rows 12..15 at 16k;
                                                                  // chroma: plane p rows 6,7 at 16p + 8k
-    uint64_t full[kDbfRows + 1][kDbfRing];                       // ring[i][k] holds the rows of its next macroblock
-    uint64_t empty[kDbfRows + 1][kDbfRing];                      // the consumer is done with ring[i][k]
+    uint64_t full[ROWS + 1][kDbfRing];                       // ring[i][k] holds the rows of its next macroblock
+    uint64_t empty[ROWS + 1][kDbfRing];                      // the consumer is done with ring[i][k]
     int ticket;
 };
 
@@ -423,8 +424,8 @@ __device__ __forceinline__ void vec_set(uint2 &v, const uint32_t *r) { v = make_
 // The macroblock rows of one CTA for one role.  C = false: luma (16 rows x 16 B per macroblock, 4 edges per
 // direction, 4 rows handed down); C = true: Cb and Cr (per plane 8 rows x 8 B, 2 edges, 2 rows handed down,
 // threads 0..3 of a stream on Cb, 4..7 on Cr).
-template <bool C>
-__device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
+template <bool C, int ROWS>
+__device__ __forceinline__ void deblock_rows(DbfSmem<ROWS> &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
                                              int grp, bool trace, bool times_on, int tk)
 {
     constexpr int NW = C ? 2 : 4;    // 32-bit words per sample row of a macroblock
@@ -439,11 +440,11 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, t = lane & 7;
     const int pl = C ? t >> 2 : 0, j = C ? t & 3 : t;  // plane; row pair (vertical edges) = column pair (horizontal edges)
-    const int row = grp * kDbfRows + w;
+    const int row = grp * ROWS + w;
     if (row >= g.mb_h) return;       // nobody waits for a row outside the picture
     const bool has_top = row > 0;
-    const bool bottom_smem = w + 1 < kDbfRows && row + 1 < g.mb_h;     // the row below is a warp of this CTA
-    const bool publishes = w + 1 == kDbfRows && row + 1 < g.mb_h;      // ... or the first row of the next CTA
+    const bool bottom_smem = w + 1 < ROWS && row + 1 < g.mb_h;     // the row below is a warp of this CTA
+    const bool publishes = w + 1 == ROWS && row + 1 < g.mb_h;      // ... or the first row of the next CTA
     const int stream = kDbfQuad * quad + sub;
     const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
     const bool act = stream < n_lanes && fd.deblock != 0;
@@ -481,7 +482,7 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
         if (act && store_a) *reinterpret_cast<Vec *>(grow + RB * m) = va;
         if (act && store_b) *reinterpret_cast<Vec *>(grow + stride + RB * m) = vb;
         if (bottom_smem || publishes) {
-            // (the CTA's last row hands over to the out thread the same way, without data: ring index kDbfRows)
+            // (the CTA's last row hands over to the out thread the same way, without data: ring index ROWS)
             mbar_wait(&sm.empty[w + 1][m & RM], ((m / kDbfRing) & 1) ^ 1);
             if (to_ring) {
                 uint8_t *slot = sm.ring[w + 1][m & RM][sub] + ring_off;
@@ -626,14 +627,14 @@ __device__ __forceinline__ void deblock_rows(DbfSmem &sm, const FrameDesc *__res
 // The "in" warp of a CTA (row group > 0): keeps ring[0] -- the rows above warp 0, which the row group above
 // stored to global memory -- up to kDbfRing macroblocks ahead of warp 0.  It alone polls the global progress
 // word of the row above, so no filtering warp ever spins on global memory.
-template <bool C>
-__device__ __forceinline__ void deblock_in_warp(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
+template <bool C, int ROWS>
+__device__ __forceinline__ void deblock_in_warp(DbfSmem<ROWS> &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int n_lanes, int quad,
                                                 int grp)
 {
     constexpr int RB = C ? 8 : 16, NR = C ? 8 : 16, RM = kDbfRing - 1;
     typedef typename DbfVec<RB / 4>::type Vec;
     const int lane = threadIdx.x & 31, sub = (lane >> 2) & 3, k = lane & 3;  // lanes 0..15: (stream, row above)
-    const int row0 = grp * kDbfRows;                 // first macroblock row of the CTA
+    const int row0 = grp * ROWS;                 // first macroblock row of the CTA
     const int stream = kDbfQuad * quad + sub;
     const FrameDesc &fd = descs[min(stream, n_lanes - 1)];
     const bool act = lane < 16 && stream < n_lanes && fd.deblock != 0;
@@ -672,33 +673,36 @@ __device__ __forceinline__ void deblock_in_warp(DbfSmem &sm, const FrameDesc *__
 // are in global memory.  It is the consumer of that row's (data-less) hand-off ring: the row's lanes store,
 // __syncwarp, lane 0 arrives (release.cta); this thread's wait acquires, and its release.gpu store of the progress
 // word is cumulative over those stores.  Whatever has arrived meanwhile is published in one go.
-__device__ __forceinline__ void deblock_out_thread(DbfSmem &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int quad, int grp, bool chroma)
+template <int ROWS>
+__device__ __forceinline__ void deblock_out_thread(DbfSmem<ROWS> &sm, const FrameDesc *__restrict__ descs, const Geometry &g, int quad, int grp, bool chroma)
 {
     constexpr int RM = kDbfRing - 1;
-    const int row_last = grp * kDbfRows + kDbfRows - 1;
+    const int row_last = grp * ROWS + ROWS - 1;
     if (row_last + 1 >= g.mb_h) return;
     int *prog = descs[kDbfQuad * quad].row_progress + (chroma ? 2 : 1) * g.mb_h + row_last;
     int m = 0;
     while (m < g.mb_w) {
-        mbar_wait(&sm.full[kDbfRows][m & RM], (m / kDbfRing) & 1);
+        mbar_wait(&sm.full[ROWS][m & RM], (m / kDbfRing) & 1);
         int hi = m + 1;
-        while (hi < g.mb_w && hi < m + kDbfRing && mbar_test(&sm.full[kDbfRows][hi & RM], (hi / kDbfRing) & 1)) hi++;
-        for (int k = m; k < hi; k++) mbar_arrive(&sm.empty[kDbfRows][k & RM]);
+        while (hi < g.mb_w && hi < m + kDbfRing && mbar_test(&sm.full[ROWS][hi & RM], (hi / kDbfRing) & 1)) hi++;
+        for (int k = m; k < hi; k++) mbar_arrive(&sm.empty[ROWS][k & RM]);
         st_release(prog, hi);   // release.gpu is cumulative over what the waits above made visible
         m = hi;
     }
 }
 
-// grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/kDbfRows) row groups.  A CTA draws its work at run time:
+// grid: 2 roles x ceil(n_lanes/4) stream quads x ceil(mb_h/ROWS) row groups.  A CTA draws its work at run time:
 //  * the role from its arrival order on its SM (first luma, second chroma, ...), so that co-resident CTAs are
 //    one luma + one chroma -- luma is the heavier role, and two luma CTAs on one SM would pace every chain below them;
 //  * (row group, quad) from a per-role ticket, row-group-major: the group above of the same quad and role always
 //    has a smaller ticket, i.e. is resident or finished.  A role whose tickets are used up falls back to the other.
 // sync: [0] intra ticket (other kernel), [1] luma ticket, [2] chroma ticket, [4 + smid] arrivals per SM
-__global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *sync, int trace_ticket)
+// ROWS = macroblock rows (filtering warps) per CTA, MINB = CTAs per SM the register budget is set for (engine knob P264B200_DBF_VARIANT)
+template <int ROWS, int MINB>
+__global__ void __launch_bounds__(32 * (ROWS + 2), MINB) deblock_kernel(const FrameDesc *__restrict__ descs, Geometry g, int n_lanes, int *sync, int trace_ticket)
 {
-    __shared__ __align__(16) DbfSmem sm;
-    const int groups = (g.mb_h + kDbfRows - 1) / kDbfRows;
+    __shared__ __align__(16) DbfSmem<ROWS> sm;
+    const int groups = (g.mb_h + ROWS - 1) / ROWS;
     if (threadIdx.x == 0) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
             u = atomicAdd(sync + 1 + role, 1);
         }
         sm.ticket = 2 * u + role;
-        for (int i = 0; i < (kDbfRows + 1) * kDbfRing; i++) {
+        for (int i = 0; i < (ROWS + 1) * kDbfRing; i++) {
             mbar_init(&sm.full[0][0] + i, 1);
             mbar_init(&sm.empty[0][0] + i, 1);
         }
@@ -727,23 +731,23 @@ __global__ void __launch_bounds__(32 * kDbfWarps, 2) deblock_kernel(const FrameD
     const bool times = trace_ticket >= 0 && tk < 2048 && threadIdx.x == 0;
     if (kDbfTraceOn && times) g_dbf_cta_ns[tk][0] = dbf_now_ns();
     const int w = threadIdx.x >> 5;
-    if (w == kDbfRows) {
+    if (w == ROWS) {
         if (grp > 0) {
             if (role == 0)
-                deblock_in_warp<false>(sm, descs, g, n_lanes, quad, grp);
+                deblock_in_warp<false, ROWS>(sm, descs, g, n_lanes, quad, grp);
             else
-                deblock_in_warp<true>(sm, descs, g, n_lanes, quad, grp);
+                deblock_in_warp<true, ROWS>(sm, descs, g, n_lanes, quad, grp);
         }
         return;
     }
-    if (w == kDbfRows + 1) {
-        if ((threadIdx.x & 31) == 0) deblock_out_thread(sm, descs, g, quad, grp, role != 0);
+    if (w == ROWS + 1) {
+        if ((threadIdx.x & 31) == 0) deblock_out_thread<ROWS>(sm, descs, g, quad, grp, role != 0);
         return;
     }
     if (role == 0)
-        deblock_rows<false>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
+        deblock_rows<false, ROWS>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
     else
-        deblock_rows<true>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
+        deblock_rows<true, ROWS>(sm, descs, g, n_lanes, quad, grp, trace, trace_ticket >= 0 && tk < 2048, tk);
     if (kDbfTraceOn && times) g_dbf_cta_ns[tk][3] = dbf_now_ns();
 }
 #endif  // P264B200_DEFINE_KERNELS

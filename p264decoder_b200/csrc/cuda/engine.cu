@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "deblock.cuh"
 #include "expand_v2.cuh"
+#include "md5.cuh"
 #include "recon_inter.cuh"
 #include "recon_intra.cuh"
 
@@ -72,6 +73,7 @@ struct p264b200_engine {
     uint8_t *d_out = nullptr;      // [lanes] tight I420 pictures for the batched download (lazy)
     size_t out_bytes = 0;
     PackSrc *d_pack = nullptr;     // [lanes][n_slots] plane origins
+    uint8_t *d_md5 = nullptr;      // [lanes][16] digests (lazy)
     DeblockSide *d_bs = nullptr;   // [lanes][n_mb]
     int *d_intra = nullptr;        // [lanes][1 + 2*n_mb]: intra runs + per-MB done epochs
     int intra_epoch = 0;
@@ -101,6 +103,9 @@ struct p264b200_engine {
     int inter_variant = 0;  // P264B200_INTER_VARIANT: CTA shape of recon_inter.  0 (default) = 8x8-macroblock tiles, 384 threads x 3 CTAs per SM
                             // (56 registers): 1.47 ms at 256 lanes; 1 = 512 threads x 2 (64 registers): 1.75 ms; 2 = 8x16 tiles, 576 x 2: 1.74 ms;
                             // 3 = 8x4 tiles, 192 x 6: 1.53 ms.  (4 CTAs per SM at 40 / 48 registers: 2.2 ms.)
+    int dbf_variant = 0;   // P264B200_DBF_VARIANT: rows per deblock CTA x CTAs per SM.  0 (default) = 8 x 2 (91 registers, 16 filtering warps per SM): 1.150 ms
+                           // at 256 lanes; 1 = 6 x 3 (80 registers, 18 warps): 1.153; 2 = 7 x 3 (72 registers, 21 warps): 1.173; also measured 4 x 4: 1.228,
+                           // 10 x 2: 1.271 -- more resident chains do not help, the kernel is bound by the ALU / L1 pipes its chains share
     bool no_side = true;   // P264B200_NO_SIDE=0: run the boundary-strength pre-pass on a side stream beside recon_inter (measured: step 2.780 ->
                            // 2.764 ms, but the pre-pass then shares the SMs for the whole 1.5 ms and the per-kernel profile stops adding up; off by default)
     int dbg = 0;  // P264B200_DBG: timing experiments only (results are wrong when set)
@@ -215,6 +220,7 @@ void p264b200_engine_destroy(p264b200_engine *e)
     cudaFree(e->d_bs);
     cudaFree(e->d_out);
     cudaFree(e->d_pack);
+    cudaFree(e->d_md5);
     cudaFree(e->d_intra);
     cudaFree(e->d_blob);
     cudaFree(e->d_v2);
@@ -264,6 +270,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     if (const char *d = getenv("P264B200_DBG")) e->dbg = atoi(d);
     if (const char *d = getenv("P264B200_TRACE")) e->trace_ticket = atoi(d);
     if (const char *d = getenv("P264B200_NO_SIDE")) e->no_side = atoi(d) != 0;
+    if (const char *d = getenv("P264B200_DBF_VARIANT")) e->dbf_variant = atoi(d);
     // measured (256 lanes x 1080p): 1 group 3.05 ms per step; 2 groups pipelined across steps (one group's deblock beside the
     // other's recon_inter, priority streams) 3.15 ms; with deblock held to one CTA per SM (P264B200_DBF_PAD=100) 3.46 ms; 4 groups
     // 3.63 ms -- both kernels lean on the same L1 / shared-memory data pipe (82 % and 67 % alone), so sharing the SMs buys nothing
@@ -337,7 +344,7 @@ int p264b200_engine_create(p264b200_engine **out, const p264b200_engine_cfg *cfg
     }
     if (const char *pad = getenv("P264B200_DBF_PAD")) e->dbf_pad_bytes = atoi(pad) * 1024;
     if (!rc && e->dbf_pad_bytes > 0 &&
-        (err = cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->dbf_pad_bytes)) != cudaSuccess)
+        (err = cudaFuncSetAttribute(deblock_kernel<kDbfRows, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->dbf_pad_bytes)) != cudaSuccess)
         fail("cudaFuncSetAttribute", err);
     for (int gi = 0; gi < e->n_groups && !rc && e->n_groups > 1; gi++) {
         if ((err = cudaStreamCreateWithPriority(&e->gstream[gi], cudaStreamNonBlocking, prio_lo)) != cudaSuccess) fail("group stream", err);
@@ -376,6 +383,18 @@ int p264b200_engine_geometry(const p264b200_engine *e, int32_t *luma_stride, int
 }  // extern "C" (reopened below)
 
 namespace {
+int ensure_pack_table(p264b200_engine *e)
+{
+    if (e->d_pack) return P264B200_OK;
+    std::vector<PackSrc> tab((size_t)e->cfg.lanes * e->cfg.n_slots);
+    for (int l = 0; l < e->cfg.lanes; l++)
+        for (int sl = 0; sl < e->cfg.n_slots; sl++)
+            for (int c = 0; c < 3; c++) tab[(size_t)l * e->cfg.n_slots + sl].plane[c] = e->plane(l, sl, c);
+    CK(cudaMalloc(&e->d_pack, tab.size() * sizeof(PackSrc)));
+    CK(cudaMemcpy(e->d_pack, tab.data(), tab.size() * sizeof(PackSrc), cudaMemcpyHostToDevice));
+    return P264B200_OK;
+}
+
 // validation + FrameDesc of one lane's picture (no copies)
 int prepare_desc(p264b200_engine *e, int step, int lane, const p264b200_frame_syntax *fs)
 {
@@ -480,11 +499,13 @@ int p264b200_stage_frames(p264b200_engine *e, int step, int n, const p264b200_fr
         if (coef_span)
             CK(cudaMemcpyAsync(e->d_coefs + s0 * e->coef_cap, fs[0].coefs, coef_span * sizeof(int16_t), cudaMemcpyHostToDevice, e->s_h2d));
     } else {
-        // worst-case sized lanes (multi-stream decoder): the gaps would dominate the transfer
-        for (int l = 0; l < n; l++)
-            if (fs[l].hdr.n_coef)
-                CK(cudaMemcpyAsync(e->d_coefs + (s0 + l) * e->coef_cap, fs[l].coefs, (size_t)fs[l].hdr.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice,
-                                   e->s_h2d));
+        // worst-case sized lanes (multi-stream decoder): the gaps would dominate the transfer, so ONE pitched copy moves the
+        // used prefix of every lane (width = the longest lane's levels, one row per lane) instead of one copy per lane
+        size_t longest = 0;
+        for (int l = 0; l < n; l++) longest = std::max(longest, (size_t)fs[l].hdr.n_coef);
+        if (longest)
+            CK(cudaMemcpy2DAsync(e->d_coefs + s0 * e->coef_cap, e->coef_cap * sizeof(int16_t), fs[0].coefs, e->coef_cap * sizeof(int16_t),
+                                 longest * sizeof(int16_t), n, cudaMemcpyHostToDevice, e->s_h2d));
     }
     CK(cudaMemcpyAsync(e->d_descs + s0, &e->h_descs[s0], (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, e->s_h2d));
     memset(&e->desc_queued[s0], 1, n);
@@ -646,7 +667,13 @@ int p264b200_recon_step(p264b200_engine *e, int step, int n_lanes)
         }
         if (dbf) {
             ProfScope p(e, K_DEBLOCK, st);
-            deblock_kernel<<<2 * ((nl + kDbfQuad - 1) / kDbfQuad) * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, G > 1 ? e->dbf_pad_bytes : 0, st>>>(descs, g, nl, tickets, e->trace_ticket);
+            const int quads = (nl + kDbfQuad - 1) / kDbfQuad;
+            const size_t dyn = G > 1 ? e->dbf_pad_bytes : 0;
+            switch (e->dbf_variant) {
+            case 1: deblock_kernel<6, 3><<<2 * quads * ((g.mb_h + 5) / 6), 32 * 8, dyn, st>>>(descs, g, nl, tickets, e->trace_ticket); break;
+            case 2: deblock_kernel<7, 3><<<2 * quads * ((g.mb_h + 6) / 7), 32 * 9, dyn, st>>>(descs, g, nl, tickets, e->trace_ticket); break;
+            default: deblock_kernel<kDbfRows, 2><<<2 * quads * ((g.mb_h + kDbfRows - 1) / kDbfRows), 32 * kDbfWarps, dyn, st>>>(descs, g, nl, tickets, e->trace_ticket); break;
+            }
         }
         {
             ProfScope p(e, K_BORDER, st);
@@ -734,13 +761,9 @@ int p264b200_frames_download(p264b200_engine *e, int n, const int32_t *slots, ui
         CK(cudaMalloc(&e->d_out, need));
         e->out_bytes = need;
     }
-    if (!e->d_pack) {
-        std::vector<PackSrc> tab((size_t)e->cfg.lanes * e->cfg.n_slots);
-        for (int l = 0; l < e->cfg.lanes; l++)
-            for (int sl = 0; sl < e->cfg.n_slots; sl++)
-                for (int c = 0; c < 3; c++) tab[(size_t)l * e->cfg.n_slots + sl].plane[c] = e->plane(l, sl, c);
-        CK(cudaMalloc(&e->d_pack, tab.size() * sizeof(PackSrc)));
-        CK(cudaMemcpy(e->d_pack, tab.data(), tab.size() * sizeof(PackSrc), cudaMemcpyHostToDevice));
+    {
+        const int r = ensure_pack_table(e);
+        if (r) return r;
     }
     PackSel sel;
     for (int l = 0; l < n; l++) {
@@ -754,6 +777,36 @@ int p264b200_frames_download(p264b200_engine *e, int n, const int32_t *slots, ui
     // the ring slots are free again as soon as the pack kernel has read them
     for (int l = 0; l < n; l++) CK(cudaEventRecord(e->ev_d2h_slot[slots[l]], e->s_d2h));
     CK(cudaMemcpyAsync(dst, e->d_out, (size_t)n * picture_bytes, cudaMemcpyDeviceToHost, e->s_d2h));
+    e->d2h_busy = true;
+    return P264B200_OK;
+}
+
+int p264b200_frame_device_planes(p264b200_engine *e, int lane, int slot, void *planes[3])
+{
+    if (!e || !planes || lane < 0 || lane >= e->cfg.lanes || slot < 0 || slot >= e->cfg.n_slots) return P264B200_EINVAL;
+    for (int c = 0; c < 3; c++) planes[c] = e->plane(lane, slot, c);
+    return P264B200_OK;
+}
+
+int p264b200_frames_md5(p264b200_engine *e, int n, const int32_t *slots, uint8_t *digests)
+{
+    if (!e || !slots || !digests || n < 1 || n > e->cfg.lanes || n > kPackMaxLanes) return P264B200_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    int r = ensure_pack_table(e);
+    if (r) return r;
+    if (!e->d_md5) CK(cudaMalloc(&e->d_md5, (size_t)e->cfg.lanes * 16));
+    PackSel sel;
+    for (int l = 0; l < n; l++) {
+        if (slots[l] < 0 || slots[l] >= e->cfg.n_slots) return P264B200_EINVAL;
+        sel.slot[l] = (uint8_t)slots[l];
+    }
+    CK(cudaStreamWaitEvent(e->s_d2h, e->ev_compute, 0));
+    e->launches++;
+    md5_i420_kernel<<<(n + 31) / 32, 32, 0, e->s_d2h>>>(e->d_pack, e->cfg.n_slots, sel, e->g, n, e->d_md5);
+    CK(cudaGetLastError());
+    // the ring slots are free again as soon as the kernel has read them
+    for (int l = 0; l < n; l++) CK(cudaEventRecord(e->ev_d2h_slot[slots[l]], e->s_d2h));
+    CK(cudaMemcpyAsync(digests, e->d_md5, (size_t)n * 16, cudaMemcpyDeviceToHost, e->s_d2h));
     e->d2h_busy = true;
     return P264B200_OK;
 }

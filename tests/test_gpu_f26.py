@@ -56,3 +56,26 @@ def test_f26_decode_annexb_api():
         if n < 12 or n % 25 == 0:
             assert O.i420_md5(y, u, v) == golden[n]
     assert n == 299
+
+
+def test_f26_verified_on_the_device_by_md5_without_picture_download():
+    """output side: three copies of f26 on three lanes, every picture verified by the MD5 the device
+    computes of its tight I420 image (16 bytes of D2H per picture instead of 152 KB) against the reference decoder's md5s;
+    the zero-copy plane addresses are distinct per lane / slot and inside the frame store"""
+    path = O.f26_path()
+    if path is None:
+        pytest.skip("oracle/_ref/f26.264 not present")
+    data = np.fromfile(path, dtype=np.uint8)
+    golden = O.f26_frame_md5s()
+    frames = list(P.Parser(verbose=False).parse_stream(data))[:60]
+    lanes = 3
+    eng = P.Engine(22, 18, n_slots=2, lanes=lanes)
+    for i, fr in enumerate(frames):
+        for l in range(lanes):
+            eng.stage(0, l, fr.syntax())
+        eng.recon_step(0, lanes)
+        got = eng.md5([fr.hdr.dst_slot] * lanes)
+        assert got == [golden[i]] * lanes, f"picture {i}"
+    planes = {tuple(eng.device_planes(l, s)) for l in range(lanes) for s in range(2)}
+    assert len(planes) == 2 * lanes and all(p[0] and p[1] and p[2] for p in planes)
+    eng.close()
