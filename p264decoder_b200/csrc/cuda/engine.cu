@@ -529,8 +529,12 @@ int p264b200_stage_frames_v2(p264b200_engine *e, int step, int n, const p264b200
     // v1-shaped FrameDesc (plane pointers, slice parameters) for every lane; the records / levels it points at are
     // written by the expansion kernel below
     for (int l = 0; l < n; l++) {
-        if (!fs[l].blob || fs[l].blob_bytes > e->blob_cap || ((uintptr_t)fs[l].blob & 15)) {
-            set_err("p264b200_stage_frames_v2: packed picture missing, misaligned or larger than the engine's bound", cudaSuccess);
+        const p264b200_frame_syntax_v2 &f = fs[l];
+        const bool sections_ok = f.off_hdr <= f.off_offs && f.off_offs <= f.off_mv && f.off_mv <= f.off_mask && f.off_mask <= f.off_level &&
+                                 f.off_level <= f.blob_bytes && f.off_offs - f.off_hdr >= n_mb * 32 && f.off_mv - f.off_offs >= n_mb * 8 &&
+                                 !((f.off_hdr | f.off_offs | f.off_mv | f.off_mask | f.off_level) & 15);
+        if (!fs[l].blob || fs[l].blob_bytes > e->blob_cap || ((uintptr_t)fs[l].blob & 15) || !sections_ok) {
+            set_err("p264b200_stage_frames_v2: packed picture missing, misaligned, larger than the engine's bound or with inconsistent section offsets", cudaSuccess);
             return P264B200_EINVAL;
         }
         p264b200_frame_syntax v1;
