@@ -10,8 +10,11 @@
 //    records are staged in shared memory once (coalesced 16-byte loads);
 //  * classification is per 8x8 QUADRANT (one thread each, 4 per macroblock instead of 16 + 8): a column of two 4x4
 //    blocks with one vector becomes a 4x8 STRIP (every partition except 8x4 / 4x4 sub-partitions), the rest stay
-//    4x4 blocks; strips and blocks are appended to per-class lists (copy / H / V / diagonal / centre+b / centre+h,
-//    core/mc.c:244-257) with one shared-memory atomic each; chroma is listed per quadrant (both planes in one item);
+//    4x4 blocks ("half" items: they run the strip body and keep its first four rows); items are counted per
+//    interpolation class (copy / H / V / diagonal / centre+b / centre+h, core/mc.c:244-257) with one shared-memory
+//    atomic each and placed back to back after a barrier, the two strips of a one-vector quadrant side by side (the
+//    lanes of a 16-wide partition then read the same cache lines in one load instruction -- the L1 data pipe charges per
+//    distinct line, tools/ubench/ldg_width.cu); chroma is listed per quadrant (both planes in one item);
 //  * a strip loads its 13 window rows ONCE for 8 output rows (a 4x4 block loads 9 for 4): 28 % fewer window loads
 //    and horizontal taps in every class with a vertical filter, and the lanes of a partition still share cache lines;
 //  * the warps of the CTA draw class-pure chunks of 32 items from the lists, heaviest class first, through a
@@ -27,7 +30,7 @@
 
 namespace p264b200 {
 
-constexpr int kTileW = 8;          // macroblocks per CTA tile row; the tile height TH (8 or 16 rows) is a kernel template parameter
+constexpr int kTileW = 8;          // macroblocks per CTA tile row; the tile height TH (4, 8 or 16 rows) is a kernel template parameter
 
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
