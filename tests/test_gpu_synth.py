@@ -198,6 +198,27 @@ def test_wire_format_v2_staging_matches_oracle():
     eng.close()
 
 
+def test_wire_format_v2_rejects_inconsistent_section_offsets():
+    """the engine checks a packed picture's section table on the host before anything is copied: EINVAL, nothing launched"""
+    import ctypes as C
+
+    mb_w, mb_h = 6, 4
+    eng = P.Engine(mb_w, mb_h, n_slots=2, lanes=1)
+    fr = P.Synth(mb_w, mb_h, seed=9, first_intra=0).next()
+    v2, blob = P.pack_v2(fr.syntax())
+    lib = P.load_library()
+    for field, value in (("off_mv", v2.off_mask + 16), ("off_level", v2.blob_bytes + 16), ("off_offs", v2.off_offs + 4), ("blob_bytes", 1 << 30)):
+        bad = P.FrameSyntaxV2.from_buffer_copy(v2)
+        setattr(bad, field, value)
+        arr = (P.FrameSyntaxV2 * 1)(bad)
+        assert lib.p264b200_stage_frames_v2(eng._e, 0, 1, arr) == -1, field   # P264B200_EINVAL
+    eng.stage_v2(0, [v2])            # the untouched picture still stages and reconstructs
+    eng.recon_step(0, 1)
+    ring = O.OracleFrames(mb_w, mb_h, 2)
+    _compare(eng.download(0, fr.hdr.dst_slot), ring.recon(fr), fr, "after the rejected calls")
+    eng.close()
+
+
 def test_batched_stage_and_packed_download_match_per_picture_path():
     """p264b200_stage_frames / p264b200_frames_download (pack kernel + one contiguous D2H) against the
     per-picture calls, pipelined over several steps without intermediate syncs."""
