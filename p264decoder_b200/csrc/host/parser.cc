@@ -608,8 +608,16 @@ void Parser::mb_skip(p264b200_mb &m, int mbx, int mby)
 }
 
 // decoder/macroblock.c:410-486: CAVLC residual of one MB, packed into the coefficient stream
-int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp_luma)
+int Parser::mb_residual(BitReader &br_in, p264b200_mb &m, int mbx, int mby, int cbp_luma)
 {
+    // (the reader is worked on as a local copy: its position and cached window then live in registers across the ~24 one-bit
+    // "empty block" probes of a macroblock instead of going through memory each time; written back on every exit)
+    BitReader br = br_in;
+    struct WriteBack {
+        BitReader &dst;
+        const BitReader &src;
+        ~WriteBack() { dst = src; }
+    } write_back{br_in, br};
     const int s4 = 4 * mb_w_, s2 = 2 * mb_w_;
     int16_t luma[16][16];  // raster block index
     int16_t dc[16], cdc[2][4], cac[8][16];
@@ -622,20 +630,32 @@ int Parser::mb_residual(BitReader &br, p264b200_mb &m, int mbx, int mby, int cbp
         const int nC = predict_nnz(nnz_y_.data(), s4, 4 * mbx, 4 * mby);
         if (cavlc_read_block(br, nC, 16, dc) < 0) return P264B200_EBITSTREAM;
     }
-    for (int i = 0; i < 16; i++) {
-        const int bx = kZx[i], by = kZy[i], b = by * 4 + bx;
-        const int gx = 4 * mbx + bx, gy = 4 * mby + by;
-        int tot = 0;
-        if (cbp_luma & (1 << (i / 4))) {
-            const int nC = predict_nnz(nnz_y_.data(), s4, gx, gy);
-            if (!cavlc_skip_empty(br, nC)) {
-                memset(luma[b], 0, sizeof(luma[b]));
-                tot = i16 ? cavlc_read_block(br, nC, 15, luma[b] + 1) : cavlc_read_block(br, nC, 16, luma[b]);
-                if (tot < 0) return P264B200_EBITSTREAM;
-            }
+    {
+        // non-zero counts of the 4x4 neighbourhood: nz[(y + 1) * 5 + (x + 1)], row / column -1 = the macroblocks above / to the left
+        // (-1 = unavailable), so that the predictor of a block is two byte loads from the stack
+        int8_t nz[25];
+        uint8_t *grid = nnz_y_.data() + (size_t)(4 * mby) * s4 + 4 * mbx;
+        for (int k = 0; k < 4; k++) {
+            nz[k + 1] = mby > 0 ? (int8_t)grid[-s4 + k] : (int8_t)-1;
+            nz[5 * (k + 1)] = mbx > 0 ? (int8_t)grid[k * s4 - 1] : (int8_t)-1;
         }
-        nnz_y_[gy * s4 + gx] = (uint8_t)tot;
-        tot_luma[b] = tot;
+        for (int i = 0; i < 16; i++) {
+            const int bx = kZx[i], by = kZy[i], b = by * 4 + bx;
+            int tot = 0;
+            if (cbp_luma & (1 << (i / 4))) {
+                const int na = nz[5 * (by + 1) + bx], nb = nz[5 * by + bx + 1];
+                const int nC = (na >= 0 && nb >= 0) ? (na + nb + 1) >> 1 : na >= 0 ? na : nb >= 0 ? nb : 0;
+                if (!cavlc_skip_empty(br, nC)) {
+                    memset(luma[b], 0, sizeof(luma[b]));
+                    tot = i16 ? cavlc_read_block(br, nC, 15, luma[b] + 1) : cavlc_read_block(br, nC, 16, luma[b]);
+                    if (tot < 0) return P264B200_EBITSTREAM;
+                }
+            }
+            nz[5 * (by + 1) + bx + 1] = (int8_t)tot;
+            tot_luma[b] = tot;
+        }
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++) grid[y * s4 + x] = (uint8_t)nz[5 * (y + 1) + x + 1];
     }
     int tot_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (m.cbp_chroma & 3) {
