@@ -190,3 +190,29 @@ def test_wire_format_v2_round_trip(kw):
             assert v2.flags & 1
         if kw == dict(first_intra=0):   # the bench-shaped stream: all partition shapes, 25 % coded blocks
             assert v2.blob_bytes * 2.5 < v1_bytes
+
+
+def test_gop_scan_written_stream_and_lane_streams_parse():
+    """closed-GOP splitter on a written stream with an IDR every 3 pictures (host only): the scan finds every GOP with its picture
+    count, each GOP begins at its parameter sets, and a GOP cut out of the stream parses on its own to the same FrameSyntax the
+    serial parse produced for those pictures (an IDR resets the parser's DPB: decoder/decoder.c:43-64)"""
+    mb_w, mb_h, n_pic = 8, 6, 11
+    syn = P.Synth(mb_w, mb_h, n_refs=1, seed=3, first_intra=1, intra_period=3, sub8x8=0, max_level=3)
+    wr = P.Writer(mb_w, mb_h)
+    for _ in range(n_pic):
+        wr.put(syn.next_syntax())
+    stream = np.frombuffer(wr.data(), dtype=np.uint8).copy()
+    gops = P.gop_scan(stream)
+    assert [n for _, n in gops] == [3, 3, 3, 2]
+    serial = list(P.Parser(verbose=False).parse_stream(stream))
+    assert len(serial) == n_pic
+    first = 0
+    for gi, (off, n) in enumerate(gops):
+        end = gops[gi + 1][0] if gi + 1 < len(gops) else len(stream)
+        assert (stream[off + 4] & 0x1f) == 7
+        alone = list(P.Parser(verbose=False).parse_stream(stream[off:end]))
+        assert len(alone) == n
+        for a, b in zip(alone, serial[first : first + n]):
+            assert np.array_equal(a.mbs.view(np.uint8), b.mbs.view(np.uint8)) and np.array_equal(a.coefs, b.coefs)
+            assert a.hdr.slice_type == b.hdr.slice_type and a.hdr.num_ref == b.hdr.num_ref
+        first += n
